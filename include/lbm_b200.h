@@ -1,0 +1,152 @@
+/*
+ * lbm_b200.h -- C ABI of the static B200 runtime (liblbm_b200.so).
+ *
+ * This is the drop-in boundary of the `generator='cuda'` backend: everything the
+ * reference does per time step in Python/NumPy/mpi4py around its generated
+ * kernels is behind these entry points, so that `Simulation.one_time_step()`
+ * (pylbm/simulation.py:392-420) becomes ONE call that only enqueues work:
+ *
+ *   lbm_sim_step            <- Simulation.one_time_step          simulation.py:392-420
+ *   lbm_sim_boundary_condition <- Simulation.boundary_condition  simulation.py:373-390
+ *   lbm_periodic            <- Array.update (halo / periodic)    storage.py:306-367, 370-420
+ *   lbm_sim_comm_init + slab exchange inside lbm_sim_step
+ *                           <- mpi4py Irecv/Isend/Waitall        storage.py:210-303, 333-367
+ *   lbm_bc_apply            <- generated bounce_back, Bouzidi_bounce_back, anti_bounce_back,
+ *                              Bouzidi_anti_bounce_back, neumann* loops
+ *                                                               boundary.py:462-464, 608-618,
+ *                                                               678-680, 745-756, 818
+ *   lbm_sim_add_bc / lbm_sim_set_rhs <- BoundaryMethod.move2gpu / set_rhs
+ *                                                               boundary.py:378-397, 421-427
+ *   lbm_array_h2d / lbm_array_d2h <- Array.__setitem__/__getitem__ device sync
+ *                                                               storage.py:126-157
+ *
+ * Conventions: extern "C", plain pointers and sizes, no torch types.  Every
+ * function returns 0 on success or a negative code (-cudaError_t, or -1000-ncclResult_t,
+ * or -2000-x for argument errors); lbm_last_error() gives the message.  Nothing throws
+ * or aborts.  The caller owns all buffers passed in; the runtime owns only what it
+ * allocates itself (device copies of boundary lists, scratch, streams, events).
+ * One host thread drives one GPU (one process per GPU); a context is not thread-safe.
+ */
+#ifndef LBM_B200_H
+#define LBM_B200_H
+
+#include <stdint.h>
+#include "lbmk.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBM_ABI_VERSION 1
+
+#define LBM_STORAGE_F64 0
+#define LBM_STORAGE_F32 1
+
+/* boundary kernels (reference routine names in comments) */
+#define LBM_BC_BOUNCE_BACK 0          /* f[s] =  f[l0] + rhs                 bounce_back              */
+#define LBM_BC_ANTI_BOUNCE_BACK 1     /* f[s] = -f[l0] + rhs                 anti_bounce_back         */
+#define LBM_BC_BOUZIDI_BOUNCE_BACK 2  /* f[s] =  d*c[l0] + (1-d)*c[l1] + rhs  Bouzidi_bounce_back (c = snapshot) */
+#define LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK 3 /* f[s] = -d*f[l0] + (1-d)*f[l1] + rhs Bouzidi_anti_bounce_back */
+#define LBM_BC_NEUMANN 4              /* f[s] =  f[l0]                       neumann, neumannx/y/z    */
+
+int lbm_abi_version(void);
+const char* lbm_last_error(void);
+
+/* ---- device and memory -------------------------------------------------- */
+int lbm_device_count(void);
+int lbm_set_device(int device);
+int lbm_device_sync(void);
+int lbm_mem_info(uint64_t* free_bytes, uint64_t* total_bytes);
+int lbm_malloc(void** ptr, uint64_t bytes);
+int lbm_free(void* ptr);
+int lbm_memset(void* ptr, int value, uint64_t bytes);
+int lbm_host_alloc(void** ptr, uint64_t bytes);   /* pinned host memory */
+int lbm_host_free(void* ptr);
+int lbm_memcpy_h2d(void* dst, const void* src, uint64_t bytes);
+int lbm_memcpy_d2h(void* dst, const void* src, uint64_t bytes);
+int lbm_memcpy_d2d(void* dst, const void* src, uint64_t bytes);
+
+/* Dense host block [nk][n0][n1][n2] of doubles <-> populations k0..k0+nk-1 of a padded
+ * device array (see lbmk_grid).  Synchronous. */
+int lbm_array_h2d(void* dev, const double* host, const lbmk_grid* g, int storage, int k0, int nk);
+int lbm_array_d2h(double* host, const void* dev, const lbmk_grid* g, int storage, int k0, int nk);
+
+/* ---- stand-alone operators (enqueue on `stream`, 0 = default stream) ------ */
+
+/* Periodic ghost update of the axes selected by axis_mask (bit a = canonical axis a),
+ * axes in increasing order so that edges/corners propagate like the reference's
+ * dimension-by-dimension exchange.  vmax[a] = ghost width of axis a. */
+int lbm_periodic(void* f, const lbmk_grid* g, int nv, int storage, const int vmax[3],
+                 int axis_mask, void* stream);
+
+/* One boundary kernel over ncond entries.  istore/iload0/iload1 are DEVICE arrays of
+ * element positions (already including population and padding: see lbmk_grid), rhs/dist
+ * DEVICE arrays of doubles (may be NULL when the kind does not use them).  two_phase != 0:
+ * all loads are done before any store (scratch: DEVICE array of ncond doubles). */
+int lbm_bc_apply(int kind, void* f, int storage, int64_t ncond, const int64_t* istore,
+                 const int64_t* iload0, const int64_t* iload1, const double* rhs,
+                 const double* dist, double* scratch, int two_phase, void* stream);
+
+/* ---- time-step object ---------------------------------------------------- */
+typedef struct lbm_sim lbm_sim;
+
+typedef struct {
+    int nv;                 /* number of populations Q                                   */
+    int storage;            /* LBM_STORAGE_*                                             */
+    lbmk_grid grid;         /* geometry; lo/hi = interior range of the fused kernel      */
+    int vmax[3];            /* ghost width per canonical axis                            */
+    int periodic_mask;      /* axes wrapped locally (bit a); axis 0 is exchanged between
+                               ranks instead once lbm_sim_comm_init was called           */
+    void* f;                /* device arrays (caller-owned)                              */
+    void* fnew;
+    lbmk_launch_fn one_time_step;  /* from the generated kernel library                  */
+    int nscalars;           /* runtime scalars of the fused kernel                       */
+    int t_index;            /* position of `t` in scalars[], or -1                       */
+    double scalars[32];
+    double t;               /* current time, advanced by dt every step                   */
+    double dt;
+    uint8_t xmask[64];      /* xmask[k] != 0: population k has v_x != 0 (exchanged)       */
+} lbm_sim_desc;
+
+lbm_sim* lbm_sim_create(const lbm_sim_desc* desc);
+void lbm_sim_destroy(lbm_sim* sim);
+
+/* Register one boundary method (order of calls = order of application, like
+ * Simulation.bc.methods).  All arrays are HOST arrays and are copied to the device.
+ * Entries are grouped in `nlevels` consecutive levels [level_ptr[i], level_ptr[i+1]);
+ * levels run one after the other, entries of a level in parallel; two_phase[i] != 0
+ * makes level i gather before it scatters.  Returns the index of the method (>= 0). */
+int lbm_sim_add_bc(lbm_sim* sim, int kind, int64_t ncond, const int64_t* istore,
+                   const int64_t* iload0, const int64_t* iload1, const double* rhs,
+                   const double* dist, int nlevels, const int64_t* level_ptr,
+                   const int* two_phase);
+int lbm_sim_set_rhs(lbm_sim* sim, int ibc, const double* rhs_host);
+int lbm_sim_set_scalars(lbm_sim* sim, const double* scalars, int nscalars);
+
+/* nsteps x (ghost update -> boundary methods -> fused pull stream+collide -> swap). */
+int lbm_sim_step(lbm_sim* sim, int nsteps);
+/* ghost update + boundary methods only, on the current f. */
+int lbm_sim_boundary_condition(lbm_sim* sim);
+int lbm_sim_sync(lbm_sim* sim);
+/* current arrays (after the swaps), time and step count */
+int lbm_sim_state(lbm_sim* sim, void** f, void** fnew, double* t, int64_t* nt);
+int lbm_sim_set_state(lbm_sim* sim, void* f, void* fnew, double t);
+/* capture pairs of steps in a CUDA graph (only when the kernel does not depend on t) */
+int lbm_sim_use_graph(lbm_sim* sim, int enable);
+/* overlap the slab exchange with the interior update (multi-GPU) */
+int lbm_sim_set_overlap(lbm_sim* sim, int enable);
+/* CUDA-event timer on the stream the kernels are launched on */
+int lbm_sim_timer_start(lbm_sim* sim);
+int lbm_sim_timer_stop(lbm_sim* sim, float* elapsed_ms);
+/* number of kernels launched by this object so far */
+int64_t lbm_sim_launch_count(lbm_sim* sim);
+void* lbm_sim_stream(lbm_sim* sim);
+
+/* ---- multi-GPU: x-slabs, one process per GPU, NCCL send/recv over NVLink ---- */
+int lbm_comm_unique_id(void* id128);   /* 128-byte ncclUniqueId, created on rank 0 */
+int lbm_sim_comm_init(lbm_sim* sim, int rank, int nranks, const void* id128);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBM_B200_H */

@@ -1,0 +1,76 @@
+/*
+ * lbmk.h -- C ABI of a *generated* per-scheme kernel library (liblbmk_<hash>.so).
+ *
+ * One such library is produced by pylbm_b200.cudagen for every scheme dictionary
+ * (nvcc, sm_100a) and replaces, for generator='cuda', the extension module that
+ * the reference builds from its generated Cython source:
+ *   - module attributes looked up by the driver: pylbm/algorithm/base.py:608-618,669-681
+ *     (transport, f2m, m2f, relaxation, equilibrium, one_time_step[, source_term])
+ *   - how they are called (kwargs by name): pylbm/symbolic.py:288-299
+ *   - how the module is built/loaded: pylbm/generator/autowrap.py:52-139
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every launcher only
+ * ENQUEUES on the given CUDA stream and returns 0, or a negative cudaError_t;
+ * the caller owns every buffer; kernels never allocate.
+ */
+#ifndef LBMK_H
+#define LBMK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LBMK_ABI_VERSION 1
+
+/*
+ * Device array geometry.  Arrays are structure-of-arrays
+ *     [population k][i0][i1][i2]       (canonical 3-D; 1-D and 2-D grids use n[0] (and n[1]) = 1)
+ * with padded rows along the fastest axis i2:
+ *     element(k, i0, i1, i2) = base + k*pstride + lead + (i0*n[1] + i1)*pitch + i2
+ * `lead` is chosen so that the first interior cell of every row is 128-byte aligned
+ * (replaces the reference's `sorder` permutation of a dense NumPy array,
+ * pylbm/storage.py:60-118).  n[] INCLUDES the ghost layers (reference: vmax per side).
+ */
+typedef struct {
+    int n[3];         /* halo-inclusive logical sizes, slowest .. fastest            */
+    int lo[3];        /* first index updated by the launch, per axis                 */
+    int hi[3];        /* one past the last index updated by the launch, per axis     */
+    int tx;           /* threads of a 128-thread block laid along i2 (power of two)  */
+    int64_t pitch;    /* elements between consecutive rows                           */
+    int64_t lead;     /* position of logical index i2 = 0 inside a row               */
+    int64_t pstride;  /* elements between consecutive populations                    */
+} lbmk_grid;
+
+/* ABI version the library was generated for. */
+int lbmk_abi_version(void);
+
+/* JSON description: {"abi", "dim", "nv", "storage", "routines": {name: {"scalars": [...],
+ * "in", "out", "inner", "ops"}}}.  `scalars` gives, in order, the names of the runtime
+ * scalars (t, dt, user parameters: pylbm/algorithm/base.py:630-667) expected in `scalars[]`. */
+const char* lbmk_describe(void);
+
+/*
+ * Per-routine launcher; `fin`/`fout` are device pointers to arrays laid out as above.
+ *   lbmk_one_time_step : fout = collide(pull-stream(fin)) on [lo, hi)   (pull.py:11-59)
+ *   lbmk_transport     : fout(x) = fin(x - v_k)                         (base.py:289-296)
+ *   lbmk_f2m / lbmk_m2f: m = M f / f = M^{-1} m on [lo, hi)             (base.py:336-379)
+ *   lbmk_equilibrium, lbmk_relaxation, lbmk_source_term: in-place on m  (base.py:395-504)
+ */
+typedef int (*lbmk_launch_fn)(const void* fin, void* fout, const lbmk_grid* g,
+                              const double* scalars, void* stream);
+
+int lbmk_one_time_step(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+int lbmk_transport(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+int lbmk_f2m(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+int lbmk_m2f(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+int lbmk_equilibrium(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+int lbmk_relaxation(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+/* only present when the scheme has source terms */
+int lbmk_source_term(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LBMK_H */

@@ -1,0 +1,406 @@
+"""
+Boundary conditions: index lists (host) and their device application.
+
+The lists are part of the parity contract and reproduce the reference's
+construction order exactly (reference: pylbm/boundary.py:23-47 per label and
+velocity, :78-160 concatenation order = labels ascending -> method dictionary
+order -> velocities of the scheme -> C order of the cells; :411-419, 508-534,
+777-784, 834-842, 858-866, 882-890 load indices; :226-235 final int32 layout;
+:421-427, 561-567, 637-643, 698-704 right-hand sides; :238-321 wall
+equilibrium).  They are built from the sparse records of domain.py instead of
+`np.where` over dense [unvtot, nx, ny, nz] arrays.
+
+Application differs by design: the reference runs one generated *sequential*
+loop per method (boundary.py:462-464 ...).  Here each method is one (or two)
+CUDA kernels over device-resident position lists.  To keep the sequential
+semantics, `schedule()` finds the (rare) entries that read or overwrite what
+another entry of the same method stores and splits the list into levels;
+levels with read/write aliasing gather into a scratch buffer before they
+scatter.  Bouzidi bounce-back reads a snapshot taken when the method starts
+(the reference's `fcopy`, boundary.py:545-549) = one gather-then-scatter level.
+"""
+
+import collections
+import types
+
+import numpy as np
+
+from . import runtime as rt
+from .storage import HostArray
+
+__all__ = [
+    "Boundary", "BoundaryMethod", "BounceBack", "BouzidiBounceBack", "AntiBounceBack",
+    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule",
+]
+
+
+def schedule(store, loads, snapshot=False):
+    """
+    Split a boundary list into parallel levels that reproduce the sequential loop.
+
+    store : positions written, in list order;  loads : list of arrays of positions read.
+    Returns (order, level_ptr, two_phase): `order` is a stable permutation grouping the
+    entries by level; level l is order[level_ptr[l]:level_ptr[l+1]]; two_phase[l] tells
+    whether level l must gather before it scatters.
+
+    Sequential semantics for entries i < j:
+      read-after-write  (store_i in loads_j)  -> level_j >  level_i   (not for snapshot reads)
+      write-after-write (store_i == store_j)  -> level_j >  level_i
+      write-after-read  (store_j in loads_i)  -> level_j >= level_i, two-phase if equal
+    """
+    store = np.asarray(store, dtype=np.int64)
+    n = store.size
+    loads = [np.asarray(l, dtype=np.int64) for l in loads]
+    level = np.zeros(n, dtype=np.int64)
+    if n == 0:
+        return np.arange(0), np.array([0, 0], dtype=np.int64), np.array([1 if snapshot else 0], dtype=np.int32)
+
+    aliased = np.zeros(n, dtype=bool)          # entry reads something some entry stores
+    for l in loads:
+        aliased |= np.isin(l, store)
+    uniq, counts = np.unique(store, return_counts=True)
+    dup_pos = uniq[counts > 1]
+    duplicated = np.isin(store, dup_pos) if dup_pos.size else np.zeros(n, dtype=bool)
+
+    if not snapshot and (aliased.any() or duplicated.any()) or (snapshot and duplicated.any()):
+        # positions involved in any hazard
+        hazard_pos = set(dup_pos.tolist())
+        if not snapshot:
+            for l in loads:
+                hazard_pos.update(l[aliased].tolist())
+        involved = np.isin(store, np.fromiter(hazard_pos, dtype=np.int64, count=len(hazard_pos)))
+        involved |= duplicated
+        if not snapshot:
+            involved |= aliased
+        idx = np.nonzero(involved)[0]
+        writers = collections.defaultdict(list)   # position -> earlier entries that store it
+        readers = collections.defaultdict(list)   # position -> earlier entries that read it
+        for i in idx:
+            lev = 0
+            si = int(store[i])
+            for j in writers.get(si, ()):                    # write-after-write
+                lev = max(lev, level[j] + 1)
+            if not snapshot:
+                for l in loads:                              # read-after-write
+                    for j in writers.get(int(l[i]), ()):
+                        lev = max(lev, level[j] + 1)
+                for j in readers.get(si, ()):                # write-after-read
+                    lev = max(lev, level[j])
+            level[i] = lev
+            writers[si].append(i)
+            if not snapshot:
+                for l in loads:
+                    readers[int(l[i])].append(i)
+
+    order = np.argsort(level, kind="stable")
+    nlev = int(level.max()) + 1
+    level_ptr = np.zeros(nlev + 1, dtype=np.int64)
+    np.cumsum(np.bincount(level, minlength=nlev), out=level_ptr[1:])
+    two_phase = np.zeros(nlev, dtype=np.int32)
+    for l in range(nlev):
+        sel = order[level_ptr[l] : level_ptr[l + 1]]
+        if snapshot:
+            two_phase[l] = 1
+        else:
+            st = store[sel]
+            two_phase[l] = int(any(np.isin(ld[sel], st).any() for ld in loads))
+    return order, level_ptr, two_phase
+
+
+class Boundary:
+    """
+    Builds, for every boundary method class used in the dictionary, the ordered
+    list of (population, cell) entries to set (reference: boundary.py:78-160).
+    `methods` is the list of BoundaryMethod instances in application order.
+    """
+
+    def __init__(self, domain, generator, dico):
+        self.domain = domain
+        stencil = domain.stencil
+        dico_bound = dico.get("boundary_conditions", {}) or {}
+        uvel = stencil.uvel
+
+        def entries(label, ku):
+            # cells whose link along the symmetric of unique velocity ku is cut by `label`,
+            # shifted to the outside cell where population ku is stored
+            vsym = stencil.unique_velocities[ku].get_symmetric()
+            num = int(stencil.unum2index[vsym.num])
+            cells, dist = domain.cells_with_flag(num, label)
+            indices = np.array(cells)
+            if indices.size != 0:
+                indices = indices + uvel[num][:, np.newaxis]
+            return indices, np.array(dist)
+
+        istore = collections.OrderedDict()
+        ilabel, distance = {}, {}
+        value_bc, time_bc = {}, {}
+        for label in domain.list_of_labels():
+            if label in [-1, -2]:
+                continue
+            if label not in dico_bound:
+                raise KeyError("no boundary condition given for the label %s" % label)
+            value_bc[label] = dico_bound[label].get("value", None)
+            time_bc[label] = dico_bound[label].get("time_bc", False)
+            for k, method in dico_bound[label]["method"].items():
+                for inumk, numk in enumerate(stencil.num[k]):
+                    indices, dist = entries(label, int(stencil.unum2index[numk]))
+                    if indices.size == 0:
+                        continue
+                    ncell = indices.shape[1]
+                    velocity = (inumk + stencil.nv_ptr[k]) * np.ones(ncell, dtype=np.int32)[np.newaxis, :]
+                    block = np.concatenate([velocity, indices])
+                    lab = label * np.ones(ncell, dtype=np.int32)
+                    if method not in istore:
+                        istore[method], ilabel[method], distance[method] = block, lab, dist
+                    else:
+                        istore[method] = np.concatenate([istore[method], block], axis=1)
+                        ilabel[method] = np.concatenate([ilabel[method], lab])
+                        distance[method] = np.concatenate([distance[method], dist])
+
+        self.methods = [
+            method(istore[method], ilabel[method], distance[method], None, stencil, value_bc, time_bc,
+                   tuple([stencil.unvtot] + list(domain.shape_halo)), generator)
+            for method in istore
+        ]
+
+
+class BoundaryMethod:
+    """
+    Attributes mirrored from the reference: `istore`, `iload` (list), `ilabel`,
+    `distance`, `rhs`, `feq`, `value_bc`, `time_bc`, and `s` for Bouzidi types.
+    """
+
+    kind = None
+    snapshot = False
+
+    def __init__(self, istore, ilabel, distance, normal, stencil, value_bc, time_bc, nspace, generator=None):
+        self.istore = istore
+        self.feq = np.zeros((int(stencil.nv_ptr[-1]), istore.shape[1]))
+        self.rhs = np.zeros(istore.shape[1])
+        self.ilabel = ilabel
+        self.distance = distance
+        self.normal = normal
+        self.stencil = stencil
+        self.value_bc, self.time_bc = {}, {}
+        for k in np.unique(self.ilabel):
+            self.value_bc[k] = value_bc[k]
+            self.time_bc[k] = time_bc[k]
+        self.iload = []
+        self.nspace = nspace
+        self.generator = generator
+        self.func, self.args, self.f, self.m, self.indices = [], [], [], [], []
+        self.device_index = None     # index of the method inside the runtime's lbm_sim
+        self._order = None
+
+    # ---- lists -------------------------------------------------------------
+    def set_iload(self):
+        raise NotImplementedError
+
+    def fix_iload(self):
+        """final (ncond, dim+1) int32 C-contiguous layout (reference: boundary.py:226-235)."""
+        self.iload = [np.ascontiguousarray(l.T, dtype=np.int32) for l in self.iload]
+        self.istore = np.ascontiguousarray(self.istore.T, dtype=np.int32)
+
+    def set_rhs(self):
+        raise NotImplementedError
+
+    def _sym_difference(self, sign):
+        k = self.istore[:, 0]
+        ksym = self.stencil.get_symmetric()[k]
+        cols = np.arange(k.size)
+        self.rhs[:] = self.feq[k, cols] + sign * self.feq[ksym, cols]
+
+    # ---- wall equilibrium ----------------------------------------------------
+    def prepare_rhs(self, simulation):
+        """equilibrium populations at the wall points for the prescribed moments
+        (reference: boundary.py:238-305).  Runs before fix_iload (istore is (dim+1, n))."""
+        nv = simulation.container.nv
+        dim = simulation.domain.dim
+        v = self.stencil.get_all_velocities()
+        for key, value in self.value_bc.items():
+            if value is None:
+                continue
+            indices = np.where(self.ilabel == key)
+            ncond = indices[0].size
+            k = self.istore[0, indices]
+            s = 1 - self.distance[indices]
+            coords = tuple()
+            for i in range(dim):
+                x = simulation.domain.coords_halo[i][self.istore[i + 1, indices]]
+                x += s * v[k, i] * simulation.domain.dx
+                x = x.ravel()
+                for _ in range(1, dim):
+                    x = x[:, np.newaxis]
+                coords += (x,)
+            nspace = [ncond] + [1] * (dim - 1)
+            m = HostArray(nv, nspace, consm=simulation.scheme.consm)
+            f = HostArray(nv, nspace, consm=simulation.scheme.consm)
+            args, func = coords, value
+            if isinstance(value, tuple):
+                func = value[0]
+                args = args + tuple(value[1])
+            if self.time_bc[key]:
+                func(f, m, 0, *args)
+            else:
+                func(f, m, *args)
+            simulation.equilibrium(m)
+            simulation.m2f(m, f)
+            self.feq[:, indices[0]] = f.array.reshape((nv, ncond))
+            if self.time_bc[key]:
+                self.func.append(func)
+                self.args.append(args)
+                self.f.append(f)
+                self.m.append(m)
+                self.indices.append(indices[0])
+
+    def update_feq(self, simulation):
+        """time-dependent boundary values (reference: boundary.py:307-321)."""
+        nv = simulation.container.nv
+        for i, func in enumerate(self.func):
+            func(self.f[i], self.m[i], simulation.t, *self.args[i])
+            simulation.equilibrium(self.m[i])
+            simulation.m2f(self.m[i], self.f[i])
+            self.feq[:, self.indices[i]] = self.f[i].array.reshape((nv, self.indices[i].size))
+
+    @property
+    def is_time_dependent(self):
+        return len(self.func) > 0
+
+    # ---- device side ---------------------------------------------------------
+    def device_lists(self, array):
+        """positions in the padded device layout + level schedule (after fix_iload)."""
+        store = array.positions(self.istore.T)
+        loads = [array.positions(l.T) for l in self.iload]
+        order, level_ptr, two_phase = schedule(store, loads, snapshot=self.snapshot)
+        self._order = order
+        return store[order], [l[order] for l in loads], level_ptr, two_phase
+
+    def move2gpu(self, sim_handle, array):
+        """register the method in the runtime (reference: boundary.py:378-397 move2gpu)."""
+        store, loads, level_ptr, two_phase = self.device_lists(array)
+        store = np.ascontiguousarray(store)
+        l0 = np.ascontiguousarray(loads[0])
+        l1 = np.ascontiguousarray(loads[1]) if len(loads) > 1 else None
+        rhs = np.ascontiguousarray(self.rhs[self._order])
+        dist = np.ascontiguousarray(self.s[self._order]) if hasattr(self, "s") else None
+        self._keep = (store, l0, l1, rhs, dist, level_ptr, two_phase)
+        idx = rt.lib().lbm_sim_add_bc(
+            sim_handle, self.kind, store.size, store.ctypes.data, l0.ctypes.data,
+            l1.ctypes.data if l1 is not None else None, rhs.ctypes.data,
+            dist.ctypes.data if dist is not None else None,
+            two_phase.size, level_ptr.ctypes.data, two_phase.ctypes.data,
+        )
+        rt.check(idx, "lbm_sim_add_bc(%s)" % type(self).__name__)
+        self.device_index = idx
+
+    def push_rhs(self, sim_handle):
+        rhs = np.ascontiguousarray(self.rhs[self._order])
+        rt.check(rt.lib().lbm_sim_set_rhs(sim_handle, self.device_index, rhs.ctypes.data), "lbm_sim_set_rhs")
+
+
+class BounceBack(BoundaryMethod):
+    """f_k(store) = f_ksym(store + v_k) + rhs (reference: boundary.py:400-469)."""
+
+    kind = rt.BC_BOUNCE_BACK
+
+    def set_iload(self):
+        k = self.istore[0]
+        ksym = self.stencil.get_symmetric()[k][np.newaxis, :]
+        v = self.stencil.get_all_velocities()
+        self.iload.append(np.concatenate([ksym, self.istore[1:] + v[k].T]))
+
+    def set_rhs(self):
+        self._sym_difference(-1)
+
+
+class BouzidiBounceBack(BoundaryMethod):
+    """Bouzidi-Firdaouss-Lallemand interpolated bounce-back (reference: boundary.py:472-623)."""
+
+    kind = rt.BC_BOUZIDI_BOUNCE_BACK
+    snapshot = True
+
+    def __init__(self, *args, **kwargs):
+        super().__init__(*args, **kwargs)
+        self.s = np.empty(self.istore.shape[1])
+
+    def set_iload(self):
+        k = self.istore[0]
+        ksym = self.stencil.get_symmetric()[k]
+        v = self.stencil.get_all_velocities()
+        iload1 = np.zeros(self.istore.shape, dtype=np.int32)
+        iload2 = np.zeros(self.istore.shape, dtype=np.int32)
+
+        near = self.distance < 0.5
+        iload1[0, near] = ksym[near]
+        iload2[0, near] = ksym[near]
+        iload1[1:, near] = self.istore[1:, near] + v[k[near]].T
+        iload2[1:, near] = self.istore[1:, near] + 2 * v[k[near]].T
+        self.s[near] = 2.0 * self.distance[near]
+
+        far = np.logical_not(near)
+        iload1[0, far] = ksym[far]
+        iload2[0, far] = k[far]
+        iload1[1:, far] = self.istore[1:, far] + v[k[far]].T
+        iload2[1:, far] = self.istore[1:, far] + v[k[far]].T
+        self.s[far] = 0.5 / self.distance[far]
+
+        self.iload.append(iload1)
+        self.iload.append(iload2)
+
+    def set_rhs(self):
+        self._sym_difference(-1)
+
+
+class AntiBounceBack(BounceBack):
+    """f_k(store) = -f_ksym(store + v_k) + rhs (reference: boundary.py:626-684)."""
+
+    kind = rt.BC_ANTI_BOUNCE_BACK
+
+    def set_rhs(self):
+        self._sym_difference(+1)
+
+
+class BouzidiAntiBounceBack(BouzidiBounceBack):
+    """interpolated anti bounce-back, in place (reference: boundary.py:687-760)."""
+
+    kind = rt.BC_BOUZIDI_ANTI_BOUNCE_BACK
+    snapshot = False
+
+    def set_rhs(self):
+        self._sym_difference(+1)
+
+
+class Neumann(BoundaryMethod):
+    """f_k(store) = f_k(store + v_k) (reference: boundary.py:763-823)."""
+
+    kind = rt.BC_NEUMANN
+    name = "neumann"
+    axis = None
+
+    def set_rhs(self):
+        pass
+
+    def set_iload(self):
+        k = self.istore[0]
+        v = self.stencil.get_all_velocities()
+        if self.axis is None:
+            indices = self.istore[1:] + v[k].T
+        else:
+            indices = self.istore[1:].copy()
+            indices[self.axis] += v[k].T[self.axis]
+        self.iload.append(np.concatenate([k[np.newaxis, :], indices]))
+
+
+class NeumannX(Neumann):
+    name = "neumannx"
+    axis = 0
+
+
+class NeumannY(Neumann):
+    name = "neumanny"
+    axis = 1
+
+
+class NeumannZ(Neumann):
+    name = "neumannz"
+    axis = 2

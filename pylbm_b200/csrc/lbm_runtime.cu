@@ -1,0 +1,732 @@
+// lbm_runtime.cu -- static B200 runtime behind include/lbm_b200.h (sm_100a).
+//
+// What the reference does per step in Python around its generated kernels
+// (pylbm/simulation.py:373-420) lives here as one enqueue-only C++ driver:
+//   periodic / slab ghost update  (pylbm/storage.py:306-367)
+//   boundary kernels              (pylbm/boundary.py:462-464, 608-618, 678-680, 745-756, 818)
+//   fused pull stream+collide     (generated library, include/lbmk.h)
+//   F <-> Fnew swap               (pylbm/simulation.py:417)
+// All kernels here are HBM/latency-bound gather/scatter or plane copies: no tensor cores.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "lbm_b200.h"
+
+// ---------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int set_error(int code, const char* what, const char* detail) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", what, detail ? detail : "");
+    return code;
+}
+
+#define CUDA_TRY(call)                                                            \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) return set_error(-(int)e_, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define ARG_ERROR(msg) set_error(-2001, "argument error", msg)
+
+extern "C" int lbm_abi_version(void) { return LBM_ABI_VERSION; }
+extern "C" const char* lbm_last_error(void) { return g_err; }
+
+// ---------------------------------------------------------------------------
+// device and memory
+// ---------------------------------------------------------------------------
+extern "C" int lbm_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) return set_error(-(int)e, "cudaGetDeviceCount", cudaGetErrorString(e));
+    return n;
+}
+extern "C" int lbm_set_device(int device) { CUDA_TRY(cudaSetDevice(device)); return 0; }
+extern "C" int lbm_device_sync(void) { CUDA_TRY(cudaDeviceSynchronize()); return 0; }
+extern "C" int lbm_mem_info(uint64_t* free_bytes, uint64_t* total_bytes) {
+    size_t f = 0, t = 0;
+    CUDA_TRY(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return 0;
+}
+extern "C" int lbm_malloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return ARG_ERROR("null ptr");
+    CUDA_TRY(cudaMalloc(ptr, bytes ? bytes : 8));
+    return 0;
+}
+extern "C" int lbm_free(void* ptr) { CUDA_TRY(cudaFree(ptr)); return 0; }
+extern "C" int lbm_memset(void* ptr, int value, uint64_t bytes) { CUDA_TRY(cudaMemset(ptr, value, bytes)); return 0; }
+extern "C" int lbm_host_alloc(void** ptr, uint64_t bytes) {
+    if (!ptr) return ARG_ERROR("null ptr");
+    CUDA_TRY(cudaMallocHost(ptr, bytes ? bytes : 8));
+    return 0;
+}
+extern "C" int lbm_host_free(void* ptr) { CUDA_TRY(cudaFreeHost(ptr)); return 0; }
+extern "C" int lbm_memcpy_h2d(void* dst, const void* src, uint64_t bytes) {
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+extern "C" int lbm_memcpy_d2h(void* dst, const void* src, uint64_t bytes) {
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+extern "C" int lbm_memcpy_d2d(void* dst, const void* src, uint64_t bytes) {
+    CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// dense host block <-> padded device array
+// ---------------------------------------------------------------------------
+template <typename S, bool TO_PADDED>
+__global__ void k_repack(S* __restrict__ padded, double* __restrict__ dense, lbmk_grid g, int k0, long long count) {
+    // dense: [nk][n0][n1][n2]; one thread per dense element of ONE population chunk
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const long long n2 = g.n[2], n1 = g.n[1];
+    const long long per_pop = (long long)g.n[0] * n1 * n2;
+    const long long k = i / per_pop;
+    const long long r = i - k * per_pop;
+    const long long i2 = r % n2;
+    const long long row = r / n2;  // i0*n1 + i1
+    const long long pos = (k0 + k) * g.pstride + g.lead + row * g.pitch + i2;
+    if (TO_PADDED)
+        padded[pos] = (S)dense[i];
+    else
+        dense[i] = (double)padded[pos];
+}
+
+template <bool TO_PADDED>
+static int repack(void* dev, double* host, const lbmk_grid* g, int storage, int k0, int nk) {
+    if (!dev || !host || !g) return ARG_ERROR("null pointer");
+    const long long per_pop = (long long)g->n[0] * g->n[1] * g->n[2];
+    // stage through a device buffer of at most ~256 MB
+    long long pops_per_chunk = (256LL << 20) / (per_pop * 8);
+    if (pops_per_chunk < 1) pops_per_chunk = 1;
+    if (pops_per_chunk > nk) pops_per_chunk = nk;
+    double* stage = nullptr;
+    CUDA_TRY(cudaMalloc(&stage, (size_t)(pops_per_chunk * per_pop * 8)));
+    int rc = 0;
+    for (long long k = 0; k < nk && rc == 0; k += pops_per_chunk) {
+        const long long nkc = (nk - k < pops_per_chunk) ? nk - k : pops_per_chunk;
+        const long long count = nkc * per_pop;
+        const unsigned blocks = (unsigned)((count + 255) / 256);
+        cudaError_t e = cudaSuccess;
+        if (TO_PADDED) {
+            e = cudaMemcpy(stage, host + k * per_pop, (size_t)count * 8, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess) {
+                if (storage == LBM_STORAGE_F64)
+                    k_repack<double, true><<<blocks, 256>>>((double*)dev, stage, *g, k0 + (int)k, count);
+                else
+                    k_repack<float, true><<<blocks, 256>>>((float*)dev, stage, *g, k0 + (int)k, count);
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        } else {
+            if (storage == LBM_STORAGE_F64)
+                k_repack<double, false><<<blocks, 256>>>((double*)dev, stage, *g, k0 + (int)k, count);
+            else
+                k_repack<float, false><<<blocks, 256>>>((float*)dev, stage, *g, k0 + (int)k, count);
+            e = cudaGetLastError();
+            if (e == cudaSuccess)
+                e = cudaMemcpy(host + k * per_pop, stage, (size_t)count * 8, cudaMemcpyDeviceToHost);
+        }
+        if (e != cudaSuccess) rc = set_error(-(int)e, "lbm_array copy", cudaGetErrorString(e));
+    }
+    cudaFree(stage);
+    return rc;
+}
+
+extern "C" int lbm_array_h2d(void* dev, const double* host, const lbmk_grid* g, int storage, int k0, int nk) {
+    return repack<true>(dev, const_cast<double*>(host), g, storage, k0, nk);
+}
+extern "C" int lbm_array_d2h(double* host, const void* dev, const lbmk_grid* g, int storage, int k0, int nk) {
+    return repack<false>(const_cast<void*>(dev), host, g, storage, k0, nk);
+}
+
+// ---------------------------------------------------------------------------
+// periodic ghost update (reference: storage.py:333-367 with one rank, 370-420 on GPU)
+// ---------------------------------------------------------------------------
+// For axis A with ghost width w:  ghost [0,w) <- [n-2w, n-w),  ghost [n-w, n) <- [w, 2w)
+// over the FULL extent of the other axes (ghosts included) and all populations, so that
+// doing the axes in increasing order fills edges and corners like the reference.
+// The extent of axis 0 can be restricted to [x0, x1) (used by the overlapped slab step).
+template <typename S, int A>
+__global__ void k_periodic(S* __restrict__ f, lbmk_grid g, int nv, int w, int x0, int x1) {
+    const long long n2 = g.n[2], n1 = g.n[1];
+    // extents of the iteration space: (k, e0, e1, e2) where axis A has extent 2w
+    const long long e0 = (A == 0) ? 2 * w : (x1 - x0);
+    const long long e1 = (A == 1) ? 2 * w : n1;
+    const long long e2 = (A == 2) ? 2 * w : n2;
+    const long long total = (long long)nv * e0 * e1 * e2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        long long r = i;
+        const long long c2 = r % e2; r /= e2;
+        const long long c1 = r % e1; r /= e1;
+        const long long c0 = r % e0; r /= e0;
+        const long long k = r;
+        long long i0 = (A == 0) ? 0 : x0 + c0, i1 = c1, i2 = c2;
+        long long j = (A == 0) ? c0 : (A == 1) ? c1 : c2;
+        const long long n = g.n[A];
+        long long dst, src;
+        if (j < w) { dst = j; src = n - 2 * w + j; }
+        else { j -= w; dst = n - w + j; src = w + j; }
+        long long d0 = i0, d1 = i1, d2 = i2, s0 = i0, s1 = i1, s2 = i2;
+        if (A == 0) { d0 = dst; s0 = src; }
+        if (A == 1) { d1 = dst; s1 = src; }
+        if (A == 2) { d2 = dst; s2 = src; }
+        const long long base = k * g.pstride + g.lead;
+        f[base + (d0 * n1 + d1) * g.pitch + d2] = f[base + (s0 * n1 + s1) * g.pitch + s2];
+    }
+}
+
+template <typename S>
+static cudaError_t launch_periodic(S* f, const lbmk_grid& g, int nv, const int vmax[3], int axis, int x0, int x1,
+                                   cudaStream_t st, int64_t* nlaunch) {
+    const int w = vmax[axis];
+    if (w <= 0 || g.n[axis] < 2 * w + 1) return cudaSuccess;
+    if (axis != 0 && x1 <= x0) return cudaSuccess;
+    long long e0 = (axis == 0) ? 2 * w : (x1 - x0);
+    long long e1 = (axis == 1) ? 2 * w : g.n[1];
+    long long e2 = (axis == 2) ? 2 * w : g.n[2];
+    long long total = (long long)nv * e0 * e1 * e2;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 64) blocks = 148LL * 64;
+    if (blocks < 1) blocks = 1;
+    if (axis == 0) k_periodic<S, 0><<<(unsigned)blocks, 256, 0, st>>>(f, g, nv, w, x0, x1);
+    if (axis == 1) k_periodic<S, 1><<<(unsigned)blocks, 256, 0, st>>>(f, g, nv, w, x0, x1);
+    if (axis == 2) k_periodic<S, 2><<<(unsigned)blocks, 256, 0, st>>>(f, g, nv, w, x0, x1);
+    if (nlaunch) ++*nlaunch;
+    return cudaGetLastError();
+}
+
+static cudaError_t periodic_axes(void* f, const lbmk_grid& g, int nv, int storage, const int vmax[3], int mask,
+                                 int x0, int x1, cudaStream_t st, int64_t* nlaunch) {
+    for (int a = 0; a < 3; ++a) {
+        if (!(mask & (1 << a))) continue;
+        cudaError_t e = (storage == LBM_STORAGE_F64)
+                            ? launch_periodic<double>((double*)f, g, nv, vmax, a, x0, x1, st, nlaunch)
+                            : launch_periodic<float>((float*)f, g, nv, vmax, a, x0, x1, st, nlaunch);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+extern "C" int lbm_periodic(void* f, const lbmk_grid* g, int nv, int storage, const int vmax[3], int axis_mask,
+                            void* stream) {
+    if (!f || !g || !vmax) return ARG_ERROR("null pointer");
+    cudaError_t e = periodic_axes(f, *g, nv, storage, vmax, axis_mask, 0, g->n[0], (cudaStream_t)stream, nullptr);
+    if (e != cudaSuccess) return set_error(-(int)e, "lbm_periodic", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// boundary kernels
+// ---------------------------------------------------------------------------
+// Arithmetic is written with explicit round-to-nearest intrinsics in the association
+// order of the reference's generated C (no FMA contraction), so fp64 results are
+// bit-identical to the sequential reference loop as long as entries are independent
+// (dependent entries are separated into levels by the host, see boundary.py).
+template <int KIND>
+__device__ __forceinline__ double bc_value(double a, double b, double rhs, double d) {
+    if (KIND == LBM_BC_BOUNCE_BACK) return __dadd_rn(a, rhs);
+    if (KIND == LBM_BC_ANTI_BOUNCE_BACK) return __dadd_rn(-a, rhs);
+    if (KIND == LBM_BC_BOUZIDI_BOUNCE_BACK)
+        return __dadd_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, d), b), __dmul_rn(d, a)), rhs);
+    if (KIND == LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK)
+        return __dadd_rn(__dadd_rn(__dmul_rn(__dsub_rn(1.0, d), b), -__dmul_rn(d, a)), rhs);
+    return a;  // Neumann
+}
+
+// PHASE 0: load + store in place; PHASE 1: load -> scratch; PHASE 2: scratch -> store
+template <typename S, int KIND, int PHASE>
+__global__ void k_bc(S* __restrict__ f, long long ncond, const long long* __restrict__ istore,
+                     const long long* __restrict__ iload0, const long long* __restrict__ iload1,
+                     const double* __restrict__ rhs, const double* __restrict__ dist, double* __restrict__ scratch) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ncond) return;
+    if (PHASE == 2) {
+        f[istore[i]] = (S)scratch[i];
+        return;
+    }
+    constexpr bool two_loads = (KIND == LBM_BC_BOUZIDI_BOUNCE_BACK || KIND == LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK);
+    const double a = (double)f[iload0[i]];
+    const double b = two_loads ? (double)f[iload1[i]] : 0.0;
+    const double r = (KIND == LBM_BC_NEUMANN) ? 0.0 : rhs[i];
+    const double d = two_loads ? dist[i] : 0.0;
+    const double v = bc_value<KIND>(a, b, r, d);
+    if (PHASE == 0)
+        f[istore[i]] = (S)v;
+    else
+        scratch[i] = v;
+}
+
+template <typename S, int KIND>
+static cudaError_t launch_bc_kind(S* f, long long n, const long long* is, const long long* l0, const long long* l1,
+                                  const double* rhs, const double* dist, double* scratch, int two_phase,
+                                  cudaStream_t st, int64_t* nlaunch) {
+    if (n <= 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    if (!two_phase) {
+        k_bc<S, KIND, 0><<<blocks, 128, 0, st>>>(f, n, is, l0, l1, rhs, dist, scratch);
+        if (nlaunch) ++*nlaunch;
+    } else {
+        k_bc<S, KIND, 1><<<blocks, 128, 0, st>>>(f, n, is, l0, l1, rhs, dist, scratch);
+        k_bc<S, KIND, 2><<<blocks, 128, 0, st>>>(f, n, is, l0, l1, rhs, dist, scratch);
+        if (nlaunch) *nlaunch += 2;
+    }
+    return cudaGetLastError();
+}
+
+template <typename S>
+static cudaError_t launch_bc(int kind, S* f, long long n, const long long* is, const long long* l0,
+                             const long long* l1, const double* rhs, const double* dist, double* scratch,
+                             int two_phase, cudaStream_t st, int64_t* nlaunch) {
+    switch (kind) {
+        case LBM_BC_BOUNCE_BACK:
+            return launch_bc_kind<S, LBM_BC_BOUNCE_BACK>(f, n, is, l0, l1, rhs, dist, scratch, two_phase, st, nlaunch);
+        case LBM_BC_ANTI_BOUNCE_BACK:
+            return launch_bc_kind<S, LBM_BC_ANTI_BOUNCE_BACK>(f, n, is, l0, l1, rhs, dist, scratch, two_phase, st, nlaunch);
+        case LBM_BC_BOUZIDI_BOUNCE_BACK:
+            return launch_bc_kind<S, LBM_BC_BOUZIDI_BOUNCE_BACK>(f, n, is, l0, l1, rhs, dist, scratch, 1, st, nlaunch);
+        case LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK:
+            return launch_bc_kind<S, LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK>(f, n, is, l0, l1, rhs, dist, scratch, two_phase, st, nlaunch);
+        case LBM_BC_NEUMANN:
+            return launch_bc_kind<S, LBM_BC_NEUMANN>(f, n, is, l0, l1, rhs, dist, scratch, two_phase, st, nlaunch);
+    }
+    return cudaErrorInvalidValue;
+}
+
+extern "C" int lbm_bc_apply(int kind, void* f, int storage, int64_t ncond, const int64_t* istore,
+                            const int64_t* iload0, const int64_t* iload1, const double* rhs, const double* dist,
+                            double* scratch, int two_phase, void* stream) {
+    if (!f || (ncond > 0 && (!istore || !iload0))) return ARG_ERROR("null pointer");
+    if ((two_phase || kind == LBM_BC_BOUZIDI_BOUNCE_BACK) && ncond > 0 && !scratch)
+        return ARG_ERROR("two-phase boundary kernel needs a scratch buffer");
+    cudaError_t e =
+        (storage == LBM_STORAGE_F64)
+            ? launch_bc<double>(kind, (double*)f, ncond, (const long long*)istore, (const long long*)iload0,
+                                (const long long*)iload1, rhs, dist, scratch, two_phase, (cudaStream_t)stream, nullptr)
+            : launch_bc<float>(kind, (float*)f, ncond, (const long long*)istore, (const long long*)iload0,
+                               (const long long*)iload1, rhs, dist, scratch, two_phase, (cudaStream_t)stream, nullptr);
+    if (e != cudaSuccess) return set_error(-(int)e, "lbm_bc_apply", cudaGetErrorString(e));
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// NCCL through dlopen (no link-time dependency; shares the copy torch already loaded)
+// ---------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid;
+typedef void* nccl_comm;
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(nccl_uid*) = nullptr;
+    int (*CommInitRank)(nccl_comm*, int, nccl_uid, int) = nullptr;
+    int (*CommDestroy)(nccl_comm) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Send)(const void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    int (*Recv)(void*, size_t, int, int, nccl_comm, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static const int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8;
+
+static int nccl_load() {
+    if (g_nccl.handle) return 0;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        g_nccl.handle = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.handle) break;
+    }
+    if (!g_nccl.handle) return set_error(-1099, "dlopen(libnccl.so.2)", dlerror());
+#define NCCL_SYM(field, name)                                                   \
+    *(void**)(&g_nccl.field) = dlsym(g_nccl.handle, name);                      \
+    if (!g_nccl.field) return set_error(-1098, "dlsym", name);
+    NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+    NCCL_SYM(CommInitRank, "ncclCommInitRank")
+    NCCL_SYM(CommDestroy, "ncclCommDestroy")
+    NCCL_SYM(GroupStart, "ncclGroupStart")
+    NCCL_SYM(GroupEnd, "ncclGroupEnd")
+    NCCL_SYM(Send, "ncclSend")
+    NCCL_SYM(Recv, "ncclRecv")
+    NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef NCCL_SYM
+    return 0;
+}
+
+#define NCCL_TRY(call)                                                                  \
+    do {                                                                                \
+        int r_ = (call);                                                                \
+        if (r_ != 0) return set_error(-1000 - r_, #call, g_nccl.GetErrorString(r_));    \
+    } while (0)
+
+extern "C" int lbm_comm_unique_id(void* id128) {
+    if (!id128) return ARG_ERROR("null id");
+    int rc = nccl_load();
+    if (rc) return rc;
+    nccl_uid id;
+    NCCL_TRY(g_nccl.GetUniqueId(&id));
+    memcpy(id128, &id, 128);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------
+// time-step object
+// ---------------------------------------------------------------------------
+struct BcMethod {
+    int kind = 0;
+    long long ncond = 0;
+    long long *istore = nullptr, *iload0 = nullptr, *iload1 = nullptr;
+    double *rhs = nullptr, *dist = nullptr;
+    std::vector<long long> level_ptr;
+    std::vector<int> two_phase;
+};
+
+struct lbm_sim {
+    lbm_sim_desc d;
+    void *f = nullptr, *fnew = nullptr;
+    double t = 0.0;
+    int64_t nt = 0;
+    std::vector<BcMethod> bcs;
+    double* scratch = nullptr;
+    long long scratch_n = 0;
+    cudaStream_t stream = nullptr, comm_stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_ready = nullptr, ev_comm = nullptr;
+    int64_t launches = 0;
+    // slab exchange
+    nccl_comm comm = nullptr;
+    int rank = 0, nranks = 1;
+    int slab_axis = 0;
+    int overlap = 0;
+    // CUDA graph of two consecutive steps (f->fnew, fnew->f)
+    int use_graph = 0;
+    cudaGraphExec_t graph = nullptr;
+    void* graph_f = nullptr;
+    int64_t graph_launches = 0;
+};
+
+extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
+    if (!desc || !desc->f || !desc->fnew || !desc->one_time_step) {
+        ARG_ERROR("lbm_sim_create: null descriptor / arrays / kernel");
+        return nullptr;
+    }
+    if (desc->nv < 1 || desc->nv > 64 || desc->nscalars < 0 || desc->nscalars > 32) {
+        ARG_ERROR("lbm_sim_create: nv must be in [1,64] and nscalars in [0,32]");
+        return nullptr;
+    }
+    lbm_sim* s = new lbm_sim();
+    s->d = *desc;
+    s->f = desc->f;
+    s->fnew = desc->fnew;
+    s->t = desc->t;
+    // slab axis = first real axis of the canonical 3-D grid
+    s->slab_axis = 0;
+    while (s->slab_axis < 2 && desc->grid.n[s->slab_axis] == 1 && desc->vmax[s->slab_axis] == 0) ++s->slab_axis;
+    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_stop);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_comm, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        set_error(-(int)e, "lbm_sim_create", cudaGetErrorString(e));
+        delete s;
+        return nullptr;
+    }
+    return s;
+}
+
+static void free_bc(BcMethod& b) {
+    cudaFree(b.istore); cudaFree(b.iload0); cudaFree(b.iload1); cudaFree(b.rhs); cudaFree(b.dist);
+}
+
+extern "C" void lbm_sim_destroy(lbm_sim* s) {
+    if (!s) return;
+    cudaStreamSynchronize(s->stream);
+    cudaStreamSynchronize(s->comm_stream);
+    if (s->graph) cudaGraphExecDestroy(s->graph);
+    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    for (auto& b : s->bcs) free_bc(b);
+    cudaFree(s->scratch);
+    cudaEventDestroy(s->ev_start); cudaEventDestroy(s->ev_stop);
+    cudaEventDestroy(s->ev_ready); cudaEventDestroy(s->ev_comm);
+    cudaStreamDestroy(s->stream); cudaStreamDestroy(s->comm_stream);
+    delete s;
+}
+
+template <typename T>
+static cudaError_t upload(T** dst, const T* src, long long n) {
+    *dst = nullptr;
+    if (!src || n <= 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(dst, (size_t)n * sizeof(T));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, (size_t)n * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+static void drop_graph(lbm_sim* s) {
+    if (s->graph) { cudaGraphExecDestroy(s->graph); s->graph = nullptr; }
+}
+
+extern "C" int lbm_sim_add_bc(lbm_sim* s, int kind, int64_t ncond, const int64_t* istore, const int64_t* iload0,
+                              const int64_t* iload1, const double* rhs, const double* dist, int nlevels,
+                              const int64_t* level_ptr, const int* two_phase) {
+    if (!s) return ARG_ERROR("null sim");
+    if (kind < 0 || kind > LBM_BC_NEUMANN) return ARG_ERROR("unknown boundary kind");
+    if (ncond < 0 || (ncond > 0 && (!istore || !iload0))) return ARG_ERROR("null boundary lists");
+    const bool two_loads = (kind == LBM_BC_BOUZIDI_BOUNCE_BACK || kind == LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK);
+    if (ncond > 0 && two_loads && (!iload1 || !dist)) return ARG_ERROR("Bouzidi needs iload1 and dist");
+    if (ncond > 0 && kind != LBM_BC_NEUMANN && !rhs) return ARG_ERROR("rhs missing");
+    BcMethod b;
+    b.kind = kind;
+    b.ncond = ncond;
+    CUDA_TRY(upload(&b.istore, (const long long*)istore, ncond));
+    CUDA_TRY(upload(&b.iload0, (const long long*)iload0, ncond));
+    CUDA_TRY(upload(&b.iload1, (const long long*)iload1, two_loads ? ncond : 0));
+    CUDA_TRY(upload(&b.rhs, rhs, kind != LBM_BC_NEUMANN ? ncond : 0));
+    CUDA_TRY(upload(&b.dist, dist, two_loads ? ncond : 0));
+    if (nlevels <= 0 || !level_ptr) {
+        b.level_ptr = {0, (long long)ncond};
+        b.two_phase = {kind == LBM_BC_BOUZIDI_BOUNCE_BACK ? 1 : 0};
+    } else {
+        b.level_ptr.assign(level_ptr, level_ptr + nlevels + 1);
+        for (int i = 0; i < nlevels; ++i) b.two_phase.push_back(two_phase ? two_phase[i] : 1);
+        if (b.level_ptr.front() != 0 || b.level_ptr.back() != ncond) return ARG_ERROR("level_ptr must span [0, ncond]");
+    }
+    long long maxlevel = 0;
+    for (size_t i = 0; i + 1 < b.level_ptr.size(); ++i) {
+        long long n = b.level_ptr[i + 1] - b.level_ptr[i];
+        if (n < 0) return ARG_ERROR("level_ptr must be non-decreasing");
+        if (n > maxlevel) maxlevel = n;
+    }
+    if (maxlevel > s->scratch_n) {
+        cudaFree(s->scratch);
+        s->scratch = nullptr;
+        CUDA_TRY(cudaMalloc(&s->scratch, (size_t)maxlevel * sizeof(double)));
+        s->scratch_n = maxlevel;
+    }
+    s->bcs.push_back(b);
+    drop_graph(s);
+    return (int)s->bcs.size() - 1;
+}
+
+extern "C" int lbm_sim_set_rhs(lbm_sim* s, int ibc, const double* rhs_host) {
+    if (!s || ibc < 0 || ibc >= (int)s->bcs.size() || !rhs_host) return ARG_ERROR("lbm_sim_set_rhs");
+    BcMethod& b = s->bcs[ibc];
+    if (b.ncond == 0 || !b.rhs) return 0;
+    CUDA_TRY(cudaMemcpyAsync(b.rhs, rhs_host, (size_t)b.ncond * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));  // rhs_host may be pageable / reused by the caller
+    return 0;
+}
+
+extern "C" int lbm_sim_set_scalars(lbm_sim* s, const double* scalars, int n) {
+    if (!s || n < 0 || n > 32 || (n > 0 && !scalars)) return ARG_ERROR("lbm_sim_set_scalars");
+    for (int i = 0; i < n; ++i) s->d.scalars[i] = scalars[i];
+    s->d.nscalars = n;
+    return 0;
+}
+
+// ---- pieces of one step -----------------------------------------------------
+static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
+    // planes [w, 2w) go to the left neighbour's right ghost, planes [n-2w, n-w) to the right
+    // neighbour's left ghost (periodic ring, like the reference's Cartesian communicator).
+    const lbmk_grid& g = s->d.grid;
+    const int a = s->slab_axis;
+    const int w = s->d.vmax[a];
+    if (w <= 0) return 0;
+    const long long n = g.n[a];
+    const long long stride = (a == 0) ? (long long)g.n[1] * g.pitch : (a == 1) ? g.pitch : 1;
+    const long long count = (long long)w * stride;
+    const int left = (s->rank + s->nranks - 1) % s->nranks, right = (s->rank + 1) % s->nranks;
+    const size_t esz = (s->d.storage == LBM_STORAGE_F64) ? 8 : 4;
+    const int dtype = (s->d.storage == LBM_STORAGE_F64) ? NCCL_FLOAT64 : NCCL_FLOAT32;
+    char* base = (char*)f;
+    NCCL_TRY(g_nccl.GroupStart());
+    for (int k = 0; k < s->d.nv; ++k) {
+        if (!s->d.xmask[k]) continue;
+        const long long p = (long long)k * g.pstride + g.lead;
+        // receives first from the right, then from the left: with 2 ranks both neighbours
+        // are the same peer and messages are matched in posting order.
+        NCCL_TRY(g_nccl.Recv(base + (p + (n - w) * stride) * esz, count, dtype, right, s->comm, st));
+        NCCL_TRY(g_nccl.Recv(base + p * esz, count, dtype, left, s->comm, st));
+        NCCL_TRY(g_nccl.Send(base + (p + w * stride) * esz, count, dtype, left, s->comm, st));
+        NCCL_TRY(g_nccl.Send(base + (p + (n - 2 * w) * stride) * esz, count, dtype, right, s->comm, st));
+    }
+    NCCL_TRY(g_nccl.GroupEnd());
+    s->launches += 1;
+    return 0;
+}
+
+static int apply_bcs(lbm_sim* s, void* f, cudaStream_t st) {
+    for (auto& b : s->bcs) {
+        for (size_t l = 0; l + 1 < b.level_ptr.size(); ++l) {
+            const long long o = b.level_ptr[l], n = b.level_ptr[l + 1] - o;
+            if (n <= 0) continue;
+            cudaError_t e =
+                (s->d.storage == LBM_STORAGE_F64)
+                    ? launch_bc<double>(b.kind, (double*)f, n, b.istore + o, b.iload0 + o,
+                                        b.iload1 ? b.iload1 + o : nullptr, b.rhs ? b.rhs + o : nullptr,
+                                        b.dist ? b.dist + o : nullptr, s->scratch, b.two_phase[l], st, &s->launches)
+                    : launch_bc<float>(b.kind, (float*)f, n, b.istore + o, b.iload0 + o,
+                                       b.iload1 ? b.iload1 + o : nullptr, b.rhs ? b.rhs + o : nullptr,
+                                       b.dist ? b.dist + o : nullptr, s->scratch, b.two_phase[l], st, &s->launches);
+            if (e != cudaSuccess) return set_error(-(int)e, "boundary kernel", cudaGetErrorString(e));
+        }
+    }
+    return 0;
+}
+
+static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
+    const lbmk_grid& g = s->d.grid;
+    int mask = s->d.periodic_mask;
+    if (s->nranks > 1) {
+        int rc = exchange_slabs(s, f, st);
+        if (rc) return rc;
+        mask &= ~(1 << s->slab_axis);
+    }
+    cudaError_t e = periodic_axes(f, g, s->d.nv, s->d.storage, s->d.vmax, mask, 0, g.n[0], st, &s->launches);
+    if (e != cudaSuccess) return set_error(-(int)e, "periodic update", cudaGetErrorString(e));
+    return 0;
+}
+
+static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) {
+    int rc = ghost_update(s, f, st);
+    if (rc) return rc;
+    rc = apply_bcs(s, f, st);
+    if (rc) return rc;
+    double scal[32];
+    for (int i = 0; i < s->d.nscalars; ++i) scal[i] = s->d.scalars[i];
+    if (s->d.t_index >= 0 && s->d.t_index < s->d.nscalars) scal[s->d.t_index] = t;
+    rc = s->d.one_time_step(f, fnew, &s->d.grid, scal, (void*)st);
+    if (rc) return set_error(rc, "one_time_step kernel launch", cudaGetErrorString((cudaError_t)(-rc)));
+    s->launches += 1;
+    return 0;
+}
+
+static int build_graph(lbm_sim* s) {
+    drop_graph(s);
+    cudaGraph_t graph = nullptr;
+    const int64_t before = s->launches;
+    CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = one_step(s, s->f, s->fnew, s->t, s->stream);
+    if (rc == 0) rc = one_step(s, s->fnew, s->f, s->t, s->stream);
+    cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+    s->graph_launches = s->launches - before;
+    s->launches = before;
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return set_error(-(int)e, "cudaStreamEndCapture", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&s->graph, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return set_error(-(int)e, "cudaGraphInstantiate", cudaGetErrorString(e));
+    s->graph_f = s->f;
+    return 0;
+}
+
+extern "C" int lbm_sim_step(lbm_sim* s, int nsteps) {
+    if (!s || nsteps < 0) return ARG_ERROR("lbm_sim_step");
+    int done = 0;
+    const bool graph_ok = s->use_graph && s->d.t_index < 0 && s->nranks == 1;
+    if (graph_ok && nsteps >= 2) {
+        if (!s->graph || s->graph_f != s->f) {
+            int rc = build_graph(s);
+            if (rc) return rc;
+        }
+        for (; done + 2 <= nsteps; done += 2) {
+            CUDA_TRY(cudaGraphLaunch(s->graph, s->stream));
+            s->launches += s->graph_launches;
+            s->t += 2 * s->d.dt;
+            s->nt += 2;
+        }
+    }
+    for (; done < nsteps; ++done) {
+        int rc = one_step(s, s->f, s->fnew, s->t, s->stream);
+        if (rc) return rc;
+        void* tmp = s->f; s->f = s->fnew; s->fnew = tmp;
+        s->t += s->d.dt;
+        s->nt += 1;
+    }
+    return 0;
+}
+
+extern "C" int lbm_sim_boundary_condition(lbm_sim* s) {
+    if (!s) return ARG_ERROR("null sim");
+    int rc = ghost_update(s, s->f, s->stream);
+    if (rc) return rc;
+    return apply_bcs(s, s->f, s->stream);
+}
+
+extern "C" int lbm_sim_sync(lbm_sim* s) {
+    if (!s) return ARG_ERROR("null sim");
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->comm_stream));
+    return 0;
+}
+
+extern "C" int lbm_sim_state(lbm_sim* s, void** f, void** fnew, double* t, int64_t* nt) {
+    if (!s) return ARG_ERROR("null sim");
+    if (f) *f = s->f;
+    if (fnew) *fnew = s->fnew;
+    if (t) *t = s->t;
+    if (nt) *nt = s->nt;
+    return 0;
+}
+
+extern "C" int lbm_sim_set_state(lbm_sim* s, void* f, void* fnew, double t) {
+    if (!s || !f || !fnew) return ARG_ERROR("lbm_sim_set_state");
+    s->f = f; s->fnew = fnew; s->t = t;
+    return 0;
+}
+
+extern "C" int lbm_sim_use_graph(lbm_sim* s, int enable) {
+    if (!s) return ARG_ERROR("null sim");
+    s->use_graph = enable ? 1 : 0;
+    if (!enable) drop_graph(s);
+    return 0;
+}
+
+extern "C" int lbm_sim_set_overlap(lbm_sim* s, int enable) {
+    if (!s) return ARG_ERROR("null sim");
+    s->overlap = enable ? 1 : 0;
+    return 0;
+}
+
+extern "C" int lbm_sim_timer_start(lbm_sim* s) {
+    if (!s) return ARG_ERROR("null sim");
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    CUDA_TRY(cudaEventRecord(s->ev_start, s->stream));
+    return 0;
+}
+
+extern "C" int lbm_sim_timer_stop(lbm_sim* s, float* ms) {
+    if (!s || !ms) return ARG_ERROR("lbm_sim_timer_stop");
+    CUDA_TRY(cudaEventRecord(s->ev_stop, s->stream));
+    CUDA_TRY(cudaEventSynchronize(s->ev_stop));
+    CUDA_TRY(cudaEventElapsedTime(ms, s->ev_start, s->ev_stop));
+    return 0;
+}
+
+extern "C" int64_t lbm_sim_launch_count(lbm_sim* s) { return s ? s->launches : 0; }
+extern "C" void* lbm_sim_stream(lbm_sim* s) { return s ? (void*)s->stream : nullptr; }
+
+extern "C" int lbm_sim_comm_init(lbm_sim* s, int rank, int nranks, const void* id128) {
+    if (!s || nranks < 1 || rank < 0 || rank >= nranks) return ARG_ERROR("lbm_sim_comm_init");
+    s->rank = rank;
+    s->nranks = nranks;
+    if (nranks == 1) return 0;
+    if (!id128) return ARG_ERROR("null unique id");
+    int rc = nccl_load();
+    if (rc) return rc;
+    nccl_uid id;
+    memcpy(&id, id128, 128);
+    NCCL_TRY(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
+    return 0;
+}

@@ -1,0 +1,332 @@
+"""
+Lowering of the per-cell kernel IR (algorithm.py) to CUDA C for sm_100a.
+
+This is the `generator='cuda'` code generator: it plays the role the
+reference's CythonCodeGen + CythonCodePrinter play for `generator='cython'`
+(reference: pylbm/generator/codegen.py:1014-1178, printing/cython.py:72-435),
+but emits hand-written-template CUDA C instead of Cython loops:
+
+* one thread per lattice cell, 128-thread blocks laid along the fastest axis so
+  that every population load/store of a warp is one coalesced 256-byte access;
+* device arrays are SoA [population][x][y][z] with padded rows whose first
+  interior cell is 128-byte aligned (see storage.py / include/lbmk.h);
+* the Q×Q moment transforms, equilibria and relaxation are straight-line
+  register code after SSA renaming + common-subexpression elimination, with
+  exact rational coefficients printed as round-trip double literals; nvcc
+  contracts a*b+c into DFMA.  No tensor cores: the step is HBM-bound
+  (2·Q·8 bytes per cell for a few hundred flops).
+
+The generated translation unit exports, per routine, a C-ABI launcher
+`int lbmk_<routine>(const void* in, void* out, const lbmk_grid* g,
+const double* scalars, void* stream)` plus `lbmk_describe` (include/lbmk.h).
+"""
+
+import hashlib
+
+import sympy as sp
+from sympy.printing.c import C99CodePrinter
+
+__all__ = ["generate_source", "CudaPrinter", "lower_statements"]
+
+ABI_VERSION = 1
+
+
+class CudaPrinter(C99CodePrinter):
+    """C printer for double arithmetic: integer powers as products, reciprocal
+    as 1.0/x, rationals and floats as round-trip double literals."""
+
+    def _print_Rational(self, expr):
+        return repr(float(sp.Float(expr, 30)))
+
+    def _print_Integer(self, expr):
+        return "%d.0" % int(expr) if int(expr) >= 0 else "(%d.0)" % int(expr)
+
+    def _print_Float(self, expr):
+        val = repr(float(expr))
+        return val if float(expr) >= 0 else "(%s)" % val
+
+    def _print_Pow(self, expr):
+        base, exp = expr.base, expr.exp
+        if exp.is_Integer:
+            n = int(exp)
+            b = self.parenthesize(base, 1000)
+            if n == -1:
+                return "(1.0/%s)" % b
+            if 0 < n <= 8:
+                return "(" + "*".join([b] * n) + ")"
+            if -8 <= n < 0:
+                return "(1.0/(" + "*".join([b] * (-n)) + "))"
+        if exp == sp.Rational(1, 2):
+            return "sqrt(%s)" % self._print(base)
+        if exp == sp.Rational(-1, 2):
+            return "rsqrt(%s)" % self._print(base)
+        return "pow(%s, %s)" % (self._print(base), self._print(exp))
+
+
+_printer = CudaPrinter()
+
+
+def _to_exact(expr):
+    """Floats -> rationals so that CSE / expansion work on exact coefficients."""
+    expr = sp.sympify(expr)
+    floats = expr.atoms(sp.Float)
+    if not floats:
+        return expr
+    return expr.xreplace({f: sp.Rational(float(f)) for f in floats})
+
+
+def lower_statements(statements, outputs, cse=True):
+    """
+    Sequential in-place statements -> SSA -> CSE.
+    Returns (list of (name, expr) temporaries in evaluation order, list of
+    output expressions).
+    """
+    current = {}
+    ssa = []
+    counter = {}
+    for lhs, rhs in statements:
+        rhs = _to_exact(sp.sympify(rhs).xreplace(current))
+        n = counter.get(lhs, 0)
+        counter[lhs] = n + 1
+        new = sp.Symbol("%s_%d" % (lhs, n), real=True)
+        current[lhs] = new
+        ssa.append((new, rhs))
+    outs = [_to_exact(sp.sympify(o).xreplace(current)) for o in outputs]
+
+    if not cse:
+        return ssa, outs
+
+    # forward-substitute trivial copies / keep the statement structure for CSE
+    exprs = [rhs for _, rhs in ssa] + outs
+    names = sp.numbered_symbols("t_", real=True)
+    repl, reduced = sp.cse(exprs, symbols=names, optimizations="basic", order="none")
+    temps = list(repl)
+    for (lhs, _), red in zip(ssa, reduced[: len(ssa)]):
+        temps.append((lhs, red))
+    # CSE temporaries may reference SSA names defined "later" in `temps`
+    # (cse pulls sub-expressions to the front); order them topologically.
+    temps = _topological(temps)
+    return temps, reduced[len(ssa) :]
+
+
+def _topological(assignments):
+    defined = {lhs: rhs for lhs, rhs in assignments}
+    order, state = [], {}
+
+    def visit(sym):
+        st = state.get(sym, 0)
+        if st == 2:
+            return
+        if st == 1:
+            raise ValueError("cyclic dependency in kernel statements at %s" % sym)
+        state[sym] = 1
+        for dep in defined[sym].free_symbols:
+            if dep in defined:
+                visit(dep)
+        state[sym] = 2
+        order.append((sym, defined[sym]))
+
+    import sys
+
+    limit = sys.getrecursionlimit()
+    sys.setrecursionlimit(max(limit, 20000))
+    try:
+        for lhs, _ in assignments:
+            visit(lhs)
+    finally:
+        sys.setrecursionlimit(limit)
+    return order
+
+
+def count_ops(temps, outs):
+    """(adds, muls, divs) of the lowered kernel, for the DESIGN roofline notes."""
+    add = mul = div = 0
+    for e in [r for _, r in temps] + list(outs):
+        for node in sp.preorder_traversal(e):
+            if node.is_Add:
+                add += len(node.args) - 1
+            elif node.is_Mul:
+                mul += len(node.args) - 1
+            elif node.is_Pow:
+                if node.exp.is_Integer and node.exp > 0:
+                    mul += int(node.exp) - 1
+                else:
+                    div += 1
+    return add, mul, div
+
+
+_HEADER = r"""// Generated by pylbm_b200.cudagen -- do not edit.  sm_100a.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LBMK_ABI_VERSION %(abi)d
+
+extern "C" {
+typedef struct {
+    int n[3];          // halo-inclusive logical sizes, canonical 3-D (slowest .. fastest)
+    int lo[3];         // loop begin per axis
+    int hi[3];         // loop end per axis
+    int tx;            // threads of a block along the fastest axis (power of two <= block size)
+    int64_t pitch;     // elements between two consecutive rows of the fastest axis
+    int64_t lead;      // position of logical index 0 inside a row
+    int64_t pstride;   // elements between two populations
+} lbmk_grid;
+}
+
+typedef %(storage)s real_f;   // storage type of the populations in HBM
+typedef double real_m;        // moments are always stored in fp64
+#define LBMK_BLOCK 128
+"""
+
+_KERNEL = r"""
+// ---------------------------------------------------------------------------
+// %(name)s : %(nin)d loads, %(nout)d stores per cell; %(ops)s
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
+lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g%(scalar_params)s)
+{
+    const int tid = threadIdx.x;
+    const int ty = LBMK_BLOCK / g.tx;
+    const int nchunk = (g.hi[2] - g.lo[2] + g.tx - 1) / g.tx;
+    const long long bid = blockIdx.x;
+    const int chunk = (int)(bid %% nchunk);
+    const long long rowblock = bid / nchunk;
+    const int i2 = g.lo[2] + chunk * g.tx + (tid & (g.tx - 1));
+    const int n1in = g.hi[1] - g.lo[1];
+    const long long row = rowblock * ty + tid / g.tx;
+    const long long nrows = (long long)(g.hi[0] - g.lo[0]) * n1in;
+    if (i2 >= g.hi[2] || row >= nrows) return;
+    const int i0 = g.lo[0] + (int)(row / n1in);
+    const int i1 = g.lo[1] + (int)(row %% n1in);
+    const long long rowstride = g.pitch;
+    const long long planestride = (long long)g.n[1] * g.pitch;
+    const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
+%(loads)s
+%(body)s
+%(stores)s
+}
+
+extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)
+{
+    const long long nrows = (long long)(g->hi[0] - g->lo[0]) * (g->hi[1] - g->lo[1]);
+    const int n2 = g->hi[2] - g->lo[2];
+    if (nrows <= 0 || n2 <= 0) return 0;
+    const int ty = LBMK_BLOCK / g->tx;
+    const long long nchunk = (n2 + g->tx - 1) / g->tx;
+    const long long nblocks = nchunk * ((nrows + ty - 1) / ty);
+    if (nblocks > 2147483647LL) return -2;
+    lbmk_kernel_%(name)s<<<(unsigned)nblocks, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
+        (const %(tin)s*)fin, (%(tout)s*)fout, *g%(scalar_args)s);
+    return -(int)cudaGetLastError();
+}
+"""
+
+
+def _offset_expr(off):
+    """element offset of a neighbour for canonical 3-D integer offset."""
+    terms = []
+    o0, o1, o2 = off
+    if o0:
+        terms.append("%d * planestride" % o0)
+    if o1:
+        terms.append("%d * rowstride" % o1)
+    if o2:
+        terms.append("%d" % o2)
+    return " + ".join(terms) if terms else "0"
+
+
+def _canonical(offset):
+    offset = tuple(int(o) for o in offset)
+    return (0,) * (3 - len(offset)) + offset
+
+
+def kernel_source(ir, storage="double", cse=True, minblocks=1):
+    temps, outs = lower_statements(ir.statements, ir.outputs, cse=cse)
+    nq = len(ir.in_syms)
+    tin = "real_m" if ir.in_array == "m" else "real_f"
+    tout = "real_m" if ir.out_array == "m" else "real_f"
+    loads = []
+    for k, (sym, off) in enumerate(zip(ir.in_syms, ir.in_offsets)):
+        loads.append(
+            "    const double %s = (double)__ldg(fin + (%d * g.pstride + cell + (%s)));"
+            % (sym, k, _offset_expr(_canonical(off)))
+        )
+    body = ["    const double %s = %s;" % (lhs, _printer.doprint(rhs)) for lhs, rhs in temps]
+    stores = [
+        "    fout[%d * g.pstride + cell] = (%s)(%s);" % (k, tout, _printer.doprint(o))
+        for k, o in enumerate(outs)
+    ]
+    add, mul, div = count_ops(temps, outs)
+    scal_params = "".join(", const double %s" % _c_name(s) for s in ir.scalars)
+    scal_args = "".join(", scalars[%d]" % i for i in range(len(ir.scalars)))
+    src = _KERNEL % dict(
+        name=ir.name,
+        tin=tin,
+        tout=tout,
+        nin=nq,
+        nout=len(outs),
+        ops="%d add, %d mul, %d div before FMA contraction" % (add, mul, div),
+        minblocks=minblocks,
+        scalar_params=scal_params,
+        scalar_args=scal_args,
+        loads="\n".join(loads),
+        body="\n".join(body),
+        stores="\n".join(stores),
+    )
+    # user symbols may not be valid C identifiers (e.g. `lambda`)
+    for s in ir.scalars:
+        if _c_name(s) != s:
+            src = _rename_identifier(src, s, _c_name(s))
+    return src, (add, mul, div)
+
+
+_C_KEYWORDS = {"lambda", "double", "int", "float", "long", "short", "register", "const", "void", "auto", "g", "fin", "fout", "cell", "tid"}
+
+
+def _c_name(name):
+    safe = "".join(ch if (ch.isalnum() or ch == "_") else "_" for ch in name)
+    if safe in _C_KEYWORDS or safe[0].isdigit():
+        safe = safe + "_"
+    return safe
+
+
+def _rename_identifier(src, old, new):
+    import re
+
+    return re.sub(r"(?<![A-Za-z0-9_])%s(?![A-Za-z0-9_])" % re.escape(old), new, src)
+
+
+_DESCRIBE = r"""
+extern "C" int lbmk_abi_version(void) { return LBMK_ABI_VERSION; }
+
+extern "C" const char* lbmk_describe(void)
+{
+    return %(json)s;
+}
+"""
+
+
+def generate_source(kernels, dim, nv, storage="double", cse=True):
+    """
+    Full translation unit for a list of KernelIR.  Returns (source, info dict).
+    """
+    import json
+
+    parts = [_HEADER % dict(abi=ABI_VERSION, storage=storage)]
+    info = {"abi": ABI_VERSION, "dim": dim, "nv": nv, "storage": storage, "routines": {}}
+    for ir in kernels:
+        src, ops = kernel_source(ir, storage=storage, cse=cse)
+        parts.append(src)
+        info["routines"][ir.name] = {
+            "scalars": list(ir.scalars),
+            "in": ir.in_array,
+            "out": ir.out_array,
+            "inner": bool(ir.inner),
+            "ops": {"add": ops[0], "mul": ops[1], "div": ops[2]},
+        }
+    text = json.dumps(info, sort_keys=True)
+    literal = '"' + text.replace("\\", "\\\\").replace('"', '\\"') + '"'
+    parts.append(_DESCRIBE % dict(json=literal))
+    source = "\n".join(parts)
+    info["hash"] = hashlib.sha256(source.encode()).hexdigest()[:20]
+    return source, info

@@ -1,0 +1,421 @@
+"""
+Simulation driver with the reference's public surface, running on one B200 per
+process through the C ABI of include/lbm_b200.h.
+
+Mirror of pylbm.simulation.Simulation (reference: pylbm/simulation.py:89-153
+construction, 155-163 _initialize, 200-243 m/F item properties, 258-320
+initialization, 322-371 kernel wrappers, 373-390 boundary_condition, 392-420
+one_time_step).  Same dictionary, same attribute names, same order of
+operations per time step; what changes is where the work happens:
+
+* the kernels come from a generated CUDA library (cudagen.py) instead of a
+  generated Cython module; F, Fnew and m stay in HBM (storage.DeviceArray);
+* `one_time_step()` is a single enqueue-only call into the runtime
+  (`lbm_sim_step`): ghost update, boundary kernels, fused pull kernel, swap.
+  Constant right-hand sides are uploaded once instead of being recomputed with
+  NumPy every step (reference: boundary.py:421-427 runs every step);
+* `run(nsteps)` enqueues many steps in one call (CUDA-graph pairs when the
+  kernels do not depend on t).
+"""
+
+import ctypes
+import os
+import types
+
+import numpy as np
+import sympy as sp
+
+from . import runtime as rt
+from . import build
+from .algorithm import PullAlgorithm
+from .boundary import Boundary
+from .cudagen import generate_source
+from .domain import Domain, SlabTopology
+from .scheme import Scheme
+from .storage import DeviceArray, HostArray
+
+__all__ = ["Simulation", "CudaContainer"]
+
+
+class _ItemProperty:
+    """`sol.m[key]` / `sol.m[key] = value` style access (reference: utils.py:26-80)."""
+
+    def __init__(self, owner, getter, setter=None):
+        self._owner, self._getter, self._setter = owner, getter, setter
+
+    def __getitem__(self, key):
+        return self._getter(self._owner, key)
+
+    def __setitem__(self, key, value):
+        if self._setter is None:
+            raise AttributeError("read-only item property")
+        self._setter(self._owner, key, value)
+
+
+class CudaContainer:
+    """m, F, Fnew in HBM (the 'cuda' entry next to the reference's Numpy/Cython/Loopy
+    containers: pylbm/container.py:10-106)."""
+
+    gpu_support = True
+
+    def __init__(self, domain, scheme, sorder=None, storage="f64"):
+        self.dim = domain.dim
+        self.mpi_topo = domain.mpi_topo
+        self.nv = int(scheme.stencil.nv_ptr[-1])
+        self.nspace = domain.global_size
+        self.vmax = list(domain.stencil.vmax)
+        self.sorder = [i for i in range(self.dim + 1)]
+        shape = domain.shape_halo
+        self.F = DeviceArray(self.nv, shape, self.vmax, storage, scheme.consm)
+        self.Fnew = DeviceArray(self.nv, shape, self.vmax, storage, scheme.consm)
+        self._m = None
+        self._storage = storage
+        self._shape = shape
+        self._consm = scheme.consm
+
+    @property
+    def m(self):
+        # moments are only materialised when somebody asks for them
+        if self._m is None:
+            self._m = DeviceArray(self.nv, self._shape, self.vmax, "f64", self._consm)
+        return self._m
+
+
+class Simulation:
+    """
+    Simulation(dico, sorder=None, dtype='float64', check_inverse=False, initialize=True,
+               slab=None, nccl_id=None)
+
+    `dico` is a pylbm dictionary (box, elements, space_step, scheme_velocity, schemes,
+    parameters, relative_velocity, init, inittype, boundary_conditions, generator,
+    codegen_option, lbm_algorithm, show_code).  `dtype='float32'` selects fp32 STORAGE of
+    the populations (arithmetic stays fp64) -- new functionality, the reference ignores
+    its dtype argument (simulation.py:89-91, storage.py:67).
+    `slab=(rank, nranks)` + `nccl_id` run this process as one x-slab of a multi-GPU run.
+    """
+
+    def __init__(self, dico, sorder=None, dtype="float64", check_inverse=False, initialize=True,
+                 slab=None, nccl_id=None):
+        generator = str(dico.get("generator", "cuda")).upper()
+        if generator != "CUDA":
+            raise ValueError(
+                "pylbm_b200 only provides generator='cuda' (got %r); there is no CPU fallback" % generator
+            )
+        rt.ensure_gpu()
+        storage = {"float64": "f64", "f64": "f64", "float32": "f32", "f32": "f32"}[str(np.dtype(dtype))
+                                                                               if not isinstance(dtype, str) else dtype]
+        self.storage = storage
+
+        rank, nranks = slab if slab is not None else (0, 1)
+        topo = None
+        if nranks > 1:
+            from .stencil import Stencil
+
+            topo = SlabTopology(Stencil.extract_dim(dico), rank, nranks)
+        self.domain = Domain(dico, need_validation=False, topology=topo)
+        self.scheme = Scheme(dico, check_inverse=check_inverse, need_validation=False)
+        if self.domain.dim != self.scheme.dim:
+            raise ValueError("Solution: the dimension of the domain and of the scheme are not the same")
+
+        self._update_m = True
+        self.t = 0.0
+        self.nt = 0
+        self.dt_ = self.domain.dx / self.scheme.la
+        self.dim = self.domain.dim
+        self.extra_parameters = {}
+        self.rank, self.nranks = rank, nranks
+
+        # ---- generated kernels -----------------------------------------
+        settings = {"m_local": True, "split": False, "check_isfluid": False}
+        user_algo = dico.get("lbm_algorithm", None) or {}
+        settings.update(user_algo.get("settings", {}))
+        self.algo = PullAlgorithm(self.scheme, settings)
+        c_storage = "double" if storage == "f64" else "float"
+        source, info = generate_source(self.algo.kernels(), self.dim, self.algo.ns, storage=c_storage)
+        if dico.get("show_code", False):
+            print(source)
+        codegen_opt = dico.get("codegen_option", None)
+        if codegen_opt and codegen_opt.get("directory"):
+            os.makedirs(os.path.realpath(codegen_opt["directory"]), exist_ok=True)
+            with open(os.path.join(os.path.realpath(codegen_opt["directory"]), "lbmk_%s.cu" % info["hash"]), "w") as fh:
+                fh.write(source)
+        self.kernels = rt.KernelLibrary(build.build_kernels(source, info["hash"]))
+        self.generator = types.SimpleNamespace(backend="CUDA", module=self.kernels)
+
+        # ---- storage ----------------------------------------------------
+        self.container = CudaContainer(self.domain, self.scheme, sorder, storage)
+        self._handle = None
+
+        # ---- boundary lists ---------------------------------------------
+        self.bc = Boundary(self.domain, self.generator, dico)
+        for method in self.bc.methods:
+            method.set_iload()
+
+        self.init_type = dico.get("inittype", "moments")
+        self.init_data = dico.get("init", None)
+        self._nccl_id = nccl_id
+        self._need_init = True
+        if initialize:
+            self._initialize()
+
+    # ------------------------------------------------------------------
+    @property
+    def dt(self):
+        if isinstance(self.dt_, sp.Expr):
+            subs = list(self.scheme.param.items()) + list(self.extra_parameters.items())
+            self.dt_ = float(self.dt_.subs(subs))
+        return self.dt_
+
+    def _scalar_values(self, name):
+        out = []
+        extra = {str(k): v for k, v in self.extra_parameters.items()}
+        for s in self.kernels.scalars(name):
+            if s == "t":
+                out.append(self.t)
+            elif s == "dt":
+                out.append(self.dt)
+            elif s in extra:
+                out.append(float(extra[s]))
+            else:
+                raise KeyError(
+                    "the kernel %s needs a value for the symbol %r: give it in 'parameters' or in "
+                    "sol.extra_parameters" % (name, s)
+                )
+        return out
+
+    # ---- runtime object -------------------------------------------------
+    def _create_handle(self):
+        F, Fnew = self.container.F, self.container.Fnew
+        desc = rt.LbmSimDesc()
+        desc.nv = F.nv
+        desc.storage = F.storage_id
+        desc.grid = F.inner_grid()
+        for a in range(3):
+            desc.vmax[a] = F.canonical_vmax[a]
+        desc.periodic_mask = sum(1 << a for a in range(3) if F.canonical_vmax[a] > 0)
+        desc.f, desc.fnew = F.ptr, Fnew.ptr
+        desc.one_time_step = self.kernels.address("one_time_step")
+        names = self.kernels.scalars("one_time_step")
+        desc.nscalars = len(names)
+        desc.t_index = names.index("t") if "t" in names else -1
+        try:
+            values = self._scalar_values("one_time_step")
+        except KeyError:
+            values = [0.0] * len(names)   # user parameters may be given later (extra_parameters)
+        for i, v in enumerate(values):
+            desc.scalars[i] = v
+        desc.t, desc.dt = self.t, self.dt
+        for k in range(F.nv):
+            desc.xmask[k] = 1
+        handle = rt.lib().lbm_sim_create(ctypes.byref(desc))
+        if not handle:
+            raise rt.LbmError("lbm_sim_create failed: %s" % rt.lib().lbm_last_error().decode())
+        self._handle = handle
+        if self.nranks > 1:
+            rt.check(rt.lib().lbm_sim_comm_init(handle, self.rank, self.nranks, self._nccl_id), "lbm_sim_comm_init")
+        self._time_dependent = False
+
+    def __del__(self):
+        handle = getattr(self, "_handle", None)
+        if handle:
+            try:
+                rt.lib().lbm_sim_destroy(handle)
+            except Exception:
+                pass
+            self._handle = None
+
+    def _initialize(self):
+        """(reference: simulation.py:155-163)"""
+        self._create_handle()
+        self.initialization()
+        for method in self.bc.methods:
+            method.prepare_rhs(self)
+            method.fix_iload()
+            method.set_rhs()
+            method.move2gpu(self._handle, self.container.F)
+        self._time_dependent = any(m.is_time_dependent for m in self.bc.methods)
+        self._need_init = False
+
+    def initialization(self):
+        """(reference: simulation.py:258-320)"""
+        coords = np.meshgrid(*(c for c in self.domain.coords_halo), sparse=True, indexing="ij")
+        if self.init_type == "moments":
+            target = self.container.m
+        elif self.init_type == "distributions":
+            target = self.container.F
+        else:
+            raise ValueError("the key `inittype` should be moments or distributions")
+        if self.init_data is None:
+            return
+        for k, v in self.init_data.items():
+            if isinstance(v, tuple):
+                f = v[0]
+                extraargs = v[1] if len(v) == 2 else ()
+                target[k] = f(*(tuple(coords) + tuple(extraargs)))
+            elif isinstance(v, types.FunctionType):
+                target[k] = v(*coords)
+            else:
+                target[k] = v
+        if self.init_type == "moments":
+            self.equilibrium()
+            self.m2f()
+        else:
+            self.f2m()
+        self.container.Fnew.copy_from(self.container.F)
+        self._update_m = self.init_type != "distributions"
+
+    # ---- whole-array kernels (reference: simulation.py:322-371) -------------
+    def _launch(self, name, src, dst, inner=False):
+        grid = src.inner_grid() if inner else src.grid
+        stream = rt.lib().lbm_sim_stream(self._handle) if self._handle else None
+        self.kernels.launch(name, src.ptr, dst.ptr, grid, self._scalar_values(name), stream)
+        if self._handle:
+            rt.check(rt.lib().lbm_sim_sync(self._handle), "sync")
+        else:
+            rt.check(rt.lib().lbm_device_sync(), "sync")
+
+    def _on_device(self, host):
+        """temporary 1-D device twin of a small HostArray (kernels are shape agnostic)."""
+        ncell = int(np.prod(host.nspace))
+        dev = DeviceArray(host.nv, (ncell,), [0], "f64")
+        dev.set(host.array.reshape(host.nv, ncell))
+        return dev
+
+    def f2m(self, **kwargs):
+        self._launch("f2m", self.container.F, self.container.m)
+
+    def m2f(self, m_user=None, f_user=None, **kwargs):
+        if m_user is not None:
+            dm = self._on_device(m_user)
+            df = DeviceArray(dm.nv, dm.nspace, [0], self.storage)
+            self._launch("m2f", dm, df)
+            f_user.array[...] = df.get().reshape(f_user.array.shape)
+            return
+        self._launch("m2f", self.container.m, self.container.F)
+
+    def equilibrium(self, m_user=None, **kwargs):
+        if m_user is not None:
+            dm = self._on_device(m_user)
+            self._launch("equilibrium", dm, dm)
+            m_user.array[...] = dm.get().reshape(m_user.array.shape)
+            return
+        self._launch("equilibrium", self.container.m, self.container.m)
+
+    def relaxation(self, **kwargs):
+        self._launch("relaxation", self.container.m, self.container.m)
+
+    def source_term(self, fraction_of_time_step=1.0, **kwargs):
+        self._launch("source_term", self.container.m, self.container.m, inner=True)
+
+    def transport(self, **kwargs):
+        F, Fnew = self.container.F, self.container.Fnew
+        self._launch("transport", F, Fnew, inner=True)
+        F.copy_from(Fnew)
+
+    # ---- item properties (reference: simulation.py:200-243) -----------------
+    def _refresh_m(self):
+        if self._update_m:
+            self._update_m = False
+            self.f2m()
+
+    @property
+    def m_halo(self):
+        def get(self_, i):
+            self_._refresh_m()
+            return self_.container.m[i]
+
+        def put(self_, i, value):
+            self_._update_m = False
+            self_.container.m[i] = value
+
+        return _ItemProperty(self, get, put)
+
+    @property
+    def m(self):
+        def get(self_, i):
+            self_._refresh_m()
+            return self_.container.m._in(i)
+
+        return _ItemProperty(self, get)
+
+    @property
+    def F_halo(self):
+        def get(self_, i):
+            return self_.container.F[i]
+
+        def put(self_, i, value):
+            self_._update_m = True
+            self_.container.F[i] = value
+
+        return _ItemProperty(self, get, put)
+
+    @property
+    def F(self):
+        return _ItemProperty(self, lambda self_, i: self_.container.F._in(i))
+
+    # ---- time stepping ------------------------------------------------------
+    def _push_scalars(self):
+        names = self.kernels.scalars("one_time_step")
+        if names and names != ["t"]:
+            values = self._scalar_values("one_time_step")
+            arr = (ctypes.c_double * len(values))(*values)
+            rt.check(rt.lib().lbm_sim_set_scalars(self._handle, arr, len(values)), "lbm_sim_set_scalars")
+
+    def _update_time_bc(self):
+        for method in self.bc.methods:
+            if method.is_time_dependent:
+                method.update_feq(self)
+                method.set_rhs()
+                method.push_rhs(self._handle)
+
+    def boundary_condition(self, **kwargs):
+        """ghost update + boundary methods on F (reference: simulation.py:373-390)."""
+        if self._need_init:
+            self._initialize()
+        self._update_time_bc()
+        rt.check(rt.lib().lbm_sim_boundary_condition(self._handle), "lbm_sim_boundary_condition")
+
+    def one_time_step(self, **kwargs):
+        """(reference: simulation.py:392-420)"""
+        if self._need_init:
+            self._initialize()
+        self._update_m = True
+        if self._time_dependent:
+            self._update_time_bc()
+        if self.extra_parameters:
+            self._push_scalars()
+        rc = rt.lib().lbm_sim_step(self._handle, 1)
+        if rc < 0:
+            rt.check(rc, "lbm_sim_step")
+        c = self.container
+        c.F, c.Fnew = c.Fnew, c.F
+        self.t += self.dt
+        self.nt += 1
+
+    def run(self, nsteps, graph=True):
+        """nsteps time steps enqueued by ONE runtime call (falls back to a Python loop when a
+        boundary value depends on time)."""
+        if self._need_init:
+            self._initialize()
+        if self._time_dependent:
+            for _ in range(nsteps):
+                self.one_time_step()
+            return
+        self._update_m = True
+        if self.extra_parameters:
+            self._push_scalars()
+        rt.check(rt.lib().lbm_sim_use_graph(self._handle, 1 if graph else 0), "lbm_sim_use_graph")
+        rt.check(rt.lib().lbm_sim_step(self._handle, int(nsteps)), "lbm_sim_step")
+        if nsteps % 2:
+            c = self.container
+            c.F, c.Fnew = c.Fnew, c.F
+        for _ in range(nsteps):
+            self.t += self.dt
+        self.nt += nsteps
+
+    def synchronize(self):
+        if self._handle:
+            rt.check(rt.lib().lbm_sim_sync(self._handle), "lbm_sim_sync")
+
+    def __repr__(self):
+        return "Simulation(generator='cuda', {}, {}, t={}, nt={})".format(self.domain, self.scheme, self.t, self.nt)
