@@ -37,6 +37,20 @@ from .storage import DeviceArray, HostArray
 __all__ = ["Simulation", "CudaContainer"]
 
 
+def build_kernel_library(scheme, settings=None, storage="f64"):
+    """
+    scheme -> per-cell kernel IR -> CUDA C -> liblbmk_<hash>.so (cached in-tree by source hash).
+    Needs nvcc but no GPU, so it is also what `__graft_entry__.build()` runs on the build box.
+    Returns (algorithm, library path, CUDA source).
+    """
+    algo_settings = {"m_local": True, "split": False, "check_isfluid": False}
+    algo_settings.update(settings or {})
+    algo = PullAlgorithm(scheme, algo_settings)
+    c_storage = "double" if storage == "f64" else "float"
+    source, info = generate_source(algo.kernels(), scheme.dim, algo.ns, storage=c_storage)
+    return algo, build.build_kernels(source, info["hash"]), source
+
+
 class _ItemProperty:
     """`sol.m[key]` / `sol.m[key] = value` style access (reference: utils.py:26-80)."""
 
@@ -126,20 +140,17 @@ class Simulation:
         self.rank, self.nranks = rank, nranks
 
         # ---- generated kernels -----------------------------------------
-        settings = {"m_local": True, "split": False, "check_isfluid": False}
         user_algo = dico.get("lbm_algorithm", None) or {}
-        settings.update(user_algo.get("settings", {}))
-        self.algo = PullAlgorithm(self.scheme, settings)
-        c_storage = "double" if storage == "f64" else "float"
-        source, info = generate_source(self.algo.kernels(), self.dim, self.algo.ns, storage=c_storage)
+        self.algo, lib_path, source = build_kernel_library(self.scheme, user_algo.get("settings", {}), storage)
         if dico.get("show_code", False):
             print(source)
         codegen_opt = dico.get("codegen_option", None)
         if codegen_opt and codegen_opt.get("directory"):
-            os.makedirs(os.path.realpath(codegen_opt["directory"]), exist_ok=True)
-            with open(os.path.join(os.path.realpath(codegen_opt["directory"]), "lbmk_%s.cu" % info["hash"]), "w") as fh:
+            outdir = os.path.realpath(codegen_opt["directory"])
+            os.makedirs(outdir, exist_ok=True)
+            with open(os.path.join(outdir, os.path.basename(lib_path)[3:-3] + ".cu"), "w") as fh:
                 fh.write(source)
-        self.kernels = rt.KernelLibrary(build.build_kernels(source, info["hash"]))
+        self.kernels = rt.KernelLibrary(lib_path)
         self.generator = types.SimpleNamespace(backend="CUDA", module=self.kernels)
 
         # ---- storage ----------------------------------------------------
