@@ -28,6 +28,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
+    # ONE CUDA runtime for the static runtime library and every generated kernel library
+    # (streams/events created by one are used by launches of the other)
+    "-cudart", "shared", "-Xlinker", "-rpath=/usr/local/cuda/lib64",
 ]
 
 
@@ -97,7 +100,7 @@ def build_kernels(source, tag, force=False, keep_source=True, extra_flags=()):
 
 def load_library(path):
     try:
-        return ctypes.CDLL(path, mode=ctypes.RTLD_GLOBAL)
+        return ctypes.CDLL(path)
     except OSError as exc:
         raise BuildError(
             "cannot load %s (%s): the CUDA extension is required, there is no CPU fallback" % (path, exc)

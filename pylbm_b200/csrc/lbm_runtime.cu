@@ -432,8 +432,10 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
     // slab axis = first real axis of the canonical 3-D grid
     s->slab_axis = 0;
     while (s->slab_axis < 2 && desc->grid.n[s->slab_axis] == 1 && desc->vmax[s->slab_axis] == 0) ++s->slab_axis;
-    cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->comm_stream, cudaStreamNonBlocking);
+    // Blocking streams: they order themselves against the legacy default stream, on which the
+    // synchronous host<->device array copies and memsets of the C ABI run.
+    cudaError_t e = cudaStreamCreate(&s->stream);
+    if (e == cudaSuccess) e = cudaStreamCreate(&s->comm_stream);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_stop);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming);

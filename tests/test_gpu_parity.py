@@ -52,7 +52,7 @@ def test_lists_and_moments(name, kw):
             assert np.array_equal(x, y)
         np.testing.assert_allclose(a.rhs, b.rhs, rtol=0, atol=1e-15)
     # initial state
-    _compare(sim, ora, 1e-14)
+    _compare(sim, ora, 1e-13)
     for _ in range(50):
         sim.one_time_step()
         ora.one_time_step()
