@@ -138,6 +138,11 @@ int lbm_sim_set_overlap(lbm_sim* sim, int enable);
 /* CUDA-event timer on the stream the kernels are launched on */
 int lbm_sim_timer_start(lbm_sim* sim);
 int lbm_sim_timer_stop(lbm_sim* sim, float* elapsed_ms);
+/* per-launch timing of the fused kernel: while enabled every fused-kernel launch is bracketed
+ * by two CUDA events on the launch stream (CUDA graphs are bypassed); profile_read returns the
+ * summed device time and the number of launches since the last read. */
+int lbm_sim_profile(lbm_sim* sim, int enable);
+int lbm_sim_profile_read(lbm_sim* sim, double* fused_ms, int64_t* nlaunch);
 /* number of kernels launched by this object so far */
 int64_t lbm_sim_launch_count(lbm_sim* sim);
 void* lbm_sim_stream(lbm_sim* sim);

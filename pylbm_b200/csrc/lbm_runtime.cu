@@ -413,6 +413,10 @@ struct lbm_sim {
     cudaGraphExec_t graph = nullptr;
     void* graph_f = nullptr;
     int64_t graph_launches = 0;
+    // optional per-launch timing of the fused kernel (CUDA events on the launch stream)
+    int profile = 0;
+    std::vector<cudaEvent_t> prof_events;   // pairs (before, after)
+    size_t prof_used = 0;
 };
 
 extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
@@ -460,6 +464,7 @@ extern "C" void lbm_sim_destroy(lbm_sim* s) {
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (auto& b : s->bcs) free_bc(b);
     cudaFree(s->scratch);
+    for (auto e : s->prof_events) cudaEventDestroy(e);
     cudaEventDestroy(s->ev_start); cudaEventDestroy(s->ev_stop);
     cudaEventDestroy(s->ev_ready); cudaEventDestroy(s->ev_comm);
     cudaStreamDestroy(s->stream); cudaStreamDestroy(s->comm_stream);
@@ -608,8 +613,23 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
     double scal[32];
     for (int i = 0; i < s->d.nscalars; ++i) scal[i] = s->d.scalars[i];
     if (s->d.t_index >= 0 && s->d.t_index < s->d.nscalars) scal[s->d.t_index] = t;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (s->profile) {
+        if (s->prof_used + 2 > s->prof_events.size()) {
+            cudaEvent_t a, b;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess)
+                return set_error(-2002, "profile", "cannot create events");
+            s->prof_events.push_back(a);
+            s->prof_events.push_back(b);
+        }
+        ev0 = s->prof_events[s->prof_used];
+        ev1 = s->prof_events[s->prof_used + 1];
+        s->prof_used += 2;
+        cudaEventRecord(ev0, st);
+    }
     rc = s->d.one_time_step(f, fnew, &s->d.grid, scal, (void*)st);
     if (rc) return set_error(rc, "one_time_step kernel launch", cudaGetErrorString((cudaError_t)(-rc)));
+    if (ev1) cudaEventRecord(ev1, st);
     s->launches += 1;
     return 0;
 }
@@ -636,7 +656,7 @@ static int build_graph(lbm_sim* s) {
 extern "C" int lbm_sim_step(lbm_sim* s, int nsteps) {
     if (!s || nsteps < 0) return ARG_ERROR("lbm_sim_step");
     int done = 0;
-    const bool graph_ok = s->use_graph && s->d.t_index < 0 && s->nranks == 1;
+    const bool graph_ok = s->use_graph && s->d.t_index < 0 && s->nranks == 1 && !s->profile;
     if (graph_ok && nsteps >= 2) {
         if (!s->graph || s->graph_f != s->f) {
             int rc = build_graph(s);
@@ -713,6 +733,28 @@ extern "C" int lbm_sim_timer_stop(lbm_sim* s, float* ms) {
     CUDA_TRY(cudaEventRecord(s->ev_stop, s->stream));
     CUDA_TRY(cudaEventSynchronize(s->ev_stop));
     CUDA_TRY(cudaEventElapsedTime(ms, s->ev_start, s->ev_stop));
+    return 0;
+}
+
+extern "C" int lbm_sim_profile(lbm_sim* s, int enable) {
+    if (!s) return ARG_ERROR("null sim");
+    s->profile = enable ? 1 : 0;
+    s->prof_used = 0;
+    return 0;
+}
+
+extern "C" int lbm_sim_profile_read(lbm_sim* s, double* fused_ms, int64_t* nlaunch) {
+    if (!s || !fused_ms || !nlaunch) return ARG_ERROR("lbm_sim_profile_read");
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    double total = 0.0;
+    for (size_t i = 0; i + 1 < s->prof_used; i += 2) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->prof_events[i], s->prof_events[i + 1]));
+        total += ms;
+    }
+    *fused_ms = total;
+    *nlaunch = (int64_t)(s->prof_used / 2);
+    s->prof_used = 0;
     return 0;
 }
 

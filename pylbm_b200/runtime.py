@@ -104,6 +104,8 @@ _SIGNATURES = {
     "lbm_sim_set_overlap": (c_int, [c_void_p, c_int]),
     "lbm_sim_timer_start": (c_int, [c_void_p]),
     "lbm_sim_timer_stop": (c_int, [c_void_p, POINTER(c_float)]),
+    "lbm_sim_profile": (c_int, [c_void_p, c_int]),
+    "lbm_sim_profile_read": (c_int, [c_void_p, POINTER(c_double), POINTER(c_int64)]),
     "lbm_sim_launch_count": (c_int64, [c_void_p]),
     "lbm_sim_stream": (c_void_p, [c_void_p]),
     "lbm_comm_unique_id": (c_int, [c_void_p]),

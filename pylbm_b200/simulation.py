@@ -94,6 +94,10 @@ class CudaContainer:
             self._m = DeviceArray(self.nv, self._shape, self.vmax, "f64", self._consm)
         return self._m
 
+    def release_m(self):
+        """free the moment array (it is rebuilt by f2m on the next `sol.m[...]`)."""
+        self._m = None
+
 
 class Simulation:
     """
@@ -273,7 +277,8 @@ class Simulation:
         else:
             self.f2m()
         self.container.Fnew.copy_from(self.container.F)
-        self._update_m = self.init_type != "distributions"
+        self._update_m = True
+        self.container.release_m()   # rebuilt on demand by f2m; frees nv * cells * 8 bytes of HBM
 
     # ---- whole-array kernels (reference: simulation.py:322-371) -------------
     def _launch(self, name, src, dst, inner=False):
