@@ -105,7 +105,9 @@ typedef struct {
     double scalars[32];
     double t;               /* current time, advanced by dt every step                   */
     double dt;
-    uint8_t xmask[64];      /* xmask[k] != 0: population k has v_x != 0 (exchanged)       */
+    int8_t vel[64][3];      /* lattice velocity of population k, canonical axes (slowest..fastest);
+                               ghost layers are refreshed only for the populations that enter
+                               the domain through them                                    */
 } lbm_sim_desc;
 
 lbm_sim* lbm_sim_create(const lbm_sim_desc* desc);
@@ -131,6 +133,9 @@ int lbm_sim_sync(lbm_sim* sim);
 /* current arrays (after the swaps), time and step count */
 int lbm_sim_state(lbm_sim* sim, void** f, void** fnew, double* t, int64_t* nt);
 int lbm_sim_set_state(lbm_sim* sim, void* f, void* fnew, double t);
+/* The fused kernel writes the periodic images of the NEXT step's ghost update, so the copy
+ * kernels are skipped after the first step.  Call this when F was modified from outside. */
+int lbm_sim_invalidate_ghosts(lbm_sim* sim);
 /* capture pairs of steps in a CUDA graph (only when the kernel does not depend on t) */
 int lbm_sim_use_graph(lbm_sim* sim, int enable);
 /* overlap the slab exchange with the interior update (multi-GPU) */

@@ -38,6 +38,10 @@ typedef struct {
     int lo[3];        /* first index updated by the launch, per axis                 */
     int hi[3];        /* one past the last index updated by the launch, per axis     */
     int tx;           /* threads of a 128-thread block laid along i2 (power of two)  */
+    int w[3];         /* ghost width per axis (interior = [w, n - w))                */
+    int wrap;         /* bit a set: lbmk_one_time_step also stores, for the cells within
+                         w of a face of axis a, their periodic images into the ghost layer
+                         (= the ghost update of the NEXT step, storage.py:333-367)    */
     int64_t pitch;    /* elements between consecutive rows                           */
     int64_t lead;     /* position of logical index i2 = 0 inside a row               */
     int64_t pstride;  /* elements between consecutive populations                    */

@@ -11,6 +11,7 @@
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -156,66 +157,72 @@ extern "C" int lbm_array_d2h(double* host, const void* dev, const lbmk_grid* g, 
 // periodic ghost update (reference: storage.py:333-367 with one rank, 370-420 on GPU)
 // ---------------------------------------------------------------------------
 // For axis A with ghost width w:  ghost [0,w) <- [n-2w, n-w),  ghost [n-w, n) <- [w, 2w)
-// over the FULL extent of the other axes (ghosts included) and all populations, so that
-// doing the axes in increasing order fills edges and corners like the reference.
-// The extent of axis 0 can be restricted to [x0, x1) (used by the overlapped slab step).
+// over the FULL extent of the other axes (ghosts included), so that doing the axes in increasing
+// order fills edges and corners like the reference.  `sel` lists the populations to copy and, for
+// each, which ghost side: the low ghost layer is only ever read for populations moving in +A, the
+// high one for populations moving in -A (see cudagen.py, periodic images), so the time-step driver
+// passes the sign-matched list; lbm_periodic() passes every population and both sides.
+// The extent of axis 0 can be restricted to [x0, x1).
+struct PopSel {
+    int n;
+    unsigned char k[64];
+    unsigned char side[64];   // bit 0: low ghost, bit 1: high ghost
+};
+
 template <typename S, int A>
-__global__ void k_periodic(S* __restrict__ f, lbmk_grid g, int nv, int w, int x0, int x1) {
+__global__ void k_periodic(S* __restrict__ f, lbmk_grid g, PopSel sel, int w, int x0, int x1) {
     const long long n2 = g.n[2], n1 = g.n[1];
-    // extents of the iteration space: (k, e0, e1, e2) where axis A has extent 2w
-    const long long e0 = (A == 0) ? 2 * w : (x1 - x0);
-    const long long e1 = (A == 1) ? 2 * w : n1;
-    const long long e2 = (A == 2) ? 2 * w : n2;
-    const long long total = (long long)nv * e0 * e1 * e2;
+    // iteration space (population entry, e0, e1, e2) where axis A has extent w
+    const long long e0 = (A == 0) ? w : (x1 - x0);
+    const long long e1 = (A == 1) ? w : n1;
+    const long long e2 = (A == 2) ? w : n2;
+    const long long total = (long long)sel.n * e0 * e1 * e2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         long long r = i;
         const long long c2 = r % e2; r /= e2;
         const long long c1 = r % e1; r /= e1;
         const long long c0 = r % e0; r /= e0;
-        const long long k = r;
-        long long i0 = (A == 0) ? 0 : x0 + c0, i1 = c1, i2 = c2;
-        long long j = (A == 0) ? c0 : (A == 1) ? c1 : c2;
+        const int p = (int)r;
+        // coordinates with the one along A left at 0 (j runs over the ghost layers of A)
+        const long long i0 = (A == 0) ? 0 : x0 + c0, i1 = (A == 1) ? 0 : c1, i2 = (A == 2) ? 0 : c2;
+        const long long j = (A == 0) ? c0 : (A == 1) ? c1 : c2;
         const long long n = g.n[A];
-        long long dst, src;
-        if (j < w) { dst = j; src = n - 2 * w + j; }
-        else { j -= w; dst = n - w + j; src = w + j; }
-        long long d0 = i0, d1 = i1, d2 = i2, s0 = i0, s1 = i1, s2 = i2;
-        if (A == 0) { d0 = dst; s0 = src; }
-        if (A == 1) { d1 = dst; s1 = src; }
-        if (A == 2) { d2 = dst; s2 = src; }
-        const long long base = k * g.pstride + g.lead;
-        f[base + (d0 * n1 + d1) * g.pitch + d2] = f[base + (s0 * n1 + s1) * g.pitch + s2];
+        const long long stride = (A == 0) ? n1 * g.pitch : (A == 1) ? g.pitch : 1;
+        S* base = f + ((long long)sel.k[p] * g.pstride + g.lead + (i0 * n1 + i1) * g.pitch + i2);
+        if (sel.side[p] & 1) base[j * stride] = base[(n - 2 * w + j) * stride];
+        if (sel.side[p] & 2) base[(n - w + j) * stride] = base[(w + j) * stride];
     }
 }
 
 template <typename S>
-static cudaError_t launch_periodic(S* f, const lbmk_grid& g, int nv, const int vmax[3], int axis, int x0, int x1,
-                                   cudaStream_t st, int64_t* nlaunch) {
+static cudaError_t launch_periodic(S* f, const lbmk_grid& g, const PopSel& sel, const int vmax[3], int axis, int x0,
+                                   int x1, cudaStream_t st, int64_t* nlaunch) {
     const int w = vmax[axis];
-    if (w <= 0 || g.n[axis] < 2 * w + 1) return cudaSuccess;
+    if (w <= 0 || g.n[axis] < 2 * w + 1 || sel.n == 0) return cudaSuccess;
     if (axis != 0 && x1 <= x0) return cudaSuccess;
-    long long e0 = (axis == 0) ? 2 * w : (x1 - x0);
-    long long e1 = (axis == 1) ? 2 * w : g.n[1];
-    long long e2 = (axis == 2) ? 2 * w : g.n[2];
-    long long total = (long long)nv * e0 * e1 * e2;
+    long long e0 = (axis == 0) ? w : (x1 - x0);
+    long long e1 = (axis == 1) ? w : g.n[1];
+    long long e2 = (axis == 2) ? w : g.n[2];
+    long long total = (long long)sel.n * e0 * e1 * e2;
     long long blocks = (total + 255) / 256;
     if (blocks > 148LL * 64) blocks = 148LL * 64;
     if (blocks < 1) blocks = 1;
-    if (axis == 0) k_periodic<S, 0><<<(unsigned)blocks, 256, 0, st>>>(f, g, nv, w, x0, x1);
-    if (axis == 1) k_periodic<S, 1><<<(unsigned)blocks, 256, 0, st>>>(f, g, nv, w, x0, x1);
-    if (axis == 2) k_periodic<S, 2><<<(unsigned)blocks, 256, 0, st>>>(f, g, nv, w, x0, x1);
+    if (axis == 0) k_periodic<S, 0><<<(unsigned)blocks, 256, 0, st>>>(f, g, sel, w, x0, x1);
+    if (axis == 1) k_periodic<S, 1><<<(unsigned)blocks, 256, 0, st>>>(f, g, sel, w, x0, x1);
+    if (axis == 2) k_periodic<S, 2><<<(unsigned)blocks, 256, 0, st>>>(f, g, sel, w, x0, x1);
     if (nlaunch) ++*nlaunch;
     return cudaGetLastError();
 }
 
-static cudaError_t periodic_axes(void* f, const lbmk_grid& g, int nv, int storage, const int vmax[3], int mask,
-                                 int x0, int x1, cudaStream_t st, int64_t* nlaunch) {
+// sel[a] = selection for axis a
+static cudaError_t periodic_axes(void* f, const lbmk_grid& g, const PopSel sel[3], int storage, const int vmax[3],
+                                 int mask, int x0, int x1, cudaStream_t st, int64_t* nlaunch) {
     for (int a = 0; a < 3; ++a) {
         if (!(mask & (1 << a))) continue;
         cudaError_t e = (storage == LBM_STORAGE_F64)
-                            ? launch_periodic<double>((double*)f, g, nv, vmax, a, x0, x1, st, nlaunch)
-                            : launch_periodic<float>((float*)f, g, nv, vmax, a, x0, x1, st, nlaunch);
+                            ? launch_periodic<double>((double*)f, g, sel[a], vmax, a, x0, x1, st, nlaunch)
+                            : launch_periodic<float>((float*)f, g, sel[a], vmax, a, x0, x1, st, nlaunch);
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
@@ -224,7 +231,13 @@ static cudaError_t periodic_axes(void* f, const lbmk_grid& g, int nv, int storag
 extern "C" int lbm_periodic(void* f, const lbmk_grid* g, int nv, int storage, const int vmax[3], int axis_mask,
                             void* stream) {
     if (!f || !g || !vmax) return ARG_ERROR("null pointer");
-    cudaError_t e = periodic_axes(f, *g, nv, storage, vmax, axis_mask, 0, g->n[0], (cudaStream_t)stream, nullptr);
+    if (nv < 1 || nv > 64) return ARG_ERROR("nv must be in [1, 64]");
+    PopSel sel[3];
+    for (int a = 0; a < 3; ++a) {
+        sel[a].n = nv;
+        for (int k = 0; k < nv; ++k) { sel[a].k[k] = (unsigned char)k; sel[a].side[k] = 3; }
+    }
+    cudaError_t e = periodic_axes(f, *g, sel, storage, vmax, axis_mask, 0, g->n[0], (cudaStream_t)stream, nullptr);
     if (e != cudaSuccess) return set_error(-(int)e, "lbm_periodic", cudaGetErrorString(e));
     return 0;
 }
@@ -412,8 +425,13 @@ struct lbm_sim {
     int use_graph = 0;
     cudaGraphExec_t graph = nullptr;
     void* graph_f = nullptr;
+    int graph_fresh = 0;
     int64_t graph_launches = 0;
     // optional per-launch timing of the fused kernel (CUDA events on the launch stream)
+    // ghost layers of `f` already hold the periodic images (written by the previous fused launch)
+    int ghost_fresh = 0;
+    int wrap_mask = 0;       // axes whose images the fused kernel writes
+    PopSel sel[3];           // sign-matched populations per axis for the copy kernels / exchange
     int profile = 0;
     std::vector<cudaEvent_t> prof_events;   // pairs (before, after)
     size_t prof_used = 0;
@@ -438,6 +456,24 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
     while (s->slab_axis < 2 && desc->grid.n[s->slab_axis] == 1 && desc->vmax[s->slab_axis] == 0) ++s->slab_axis;
     // Blocking streams: they order themselves against the legacy default stream, on which the
     // synchronous host<->device array copies and memsets of the C ABI run.
+    for (int a = 0; a < 3; ++a) {
+        const int w = desc->vmax[a];
+        if ((desc->periodic_mask & (1 << a)) && w > 0 && desc->grid.n[a] - 2 * w >= 2 * w) s->wrap_mask |= (1 << a);
+    }
+    // the fastest axis is refreshed by a lean copy kernel instead: its two boundary lanes per row would
+    // stretch the lifetime of half of the blocks of the fused kernel (measured: +0.3 ms at 512^3)
+    s->wrap_mask &= ~(1 << 2);
+    if (getenv("PYLBM_B200_NO_WRAP")) s->wrap_mask = 0;
+    for (int a = 0; a < 3; ++a) {
+        s->sel[a].n = 0;
+        for (int k = 0; k < desc->nv; ++k) {
+            const int v = desc->vel[k][a];
+            if (v == 0) continue;
+            s->sel[a].k[s->sel[a].n] = (unsigned char)k;
+            s->sel[a].side[s->sel[a].n] = (v > 0) ? 1 : 2;
+            s->sel[a].n++;
+        }
+    }   // debugging aid: use the copy kernels every step
     cudaError_t e = cudaStreamCreate(&s->stream);
     if (e == cudaSuccess) e = cudaStreamCreate(&s->comm_stream);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
@@ -558,15 +594,16 @@ static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
     const int dtype = (s->d.storage == LBM_STORAGE_F64) ? NCCL_FLOAT64 : NCCL_FLOAT32;
     char* base = (char*)f;
     NCCL_TRY(g_nccl.GroupStart());
-    for (int k = 0; k < s->d.nv; ++k) {
-        if (!s->d.xmask[k]) continue;
-        const long long p = (long long)k * g.pstride + g.lead;
-        // receives first from the right, then from the left: with 2 ranks both neighbours
-        // are the same peer and messages are matched in posting order.
-        NCCL_TRY(g_nccl.Recv(base + (p + (n - w) * stride) * esz, count, dtype, right, s->comm, st));
-        NCCL_TRY(g_nccl.Recv(base + p * esz, count, dtype, left, s->comm, st));
-        NCCL_TRY(g_nccl.Send(base + (p + w * stride) * esz, count, dtype, left, s->comm, st));
-        NCCL_TRY(g_nccl.Send(base + (p + (n - 2 * w) * stride) * esz, count, dtype, right, s->comm, st));
+    const PopSel& sel = s->sel[a];
+    for (int i = 0; i < sel.n; ++i) {
+        const long long p = (long long)sel.k[i] * g.pstride + g.lead;
+        // receives first from the right, then from the left: with 2 ranks both neighbours are the
+        // same peer and messages are matched in posting order.  The high ghost layer is only read
+        // for populations moving in -axis (side bit 1), the low one for +axis (side bit 0).
+        if (sel.side[i] & 2) NCCL_TRY(g_nccl.Recv(base + (p + (n - w) * stride) * esz, count, dtype, right, s->comm, st));
+        if (sel.side[i] & 1) NCCL_TRY(g_nccl.Recv(base + p * esz, count, dtype, left, s->comm, st));
+        if (sel.side[i] & 2) NCCL_TRY(g_nccl.Send(base + (p + w * stride) * esz, count, dtype, left, s->comm, st));
+        if (sel.side[i] & 1) NCCL_TRY(g_nccl.Send(base + (p + (n - 2 * w) * stride) * esz, count, dtype, right, s->comm, st));
     }
     NCCL_TRY(g_nccl.GroupEnd());
     s->launches += 1;
@@ -600,7 +637,8 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
         if (rc) return rc;
         mask &= ~(1 << s->slab_axis);
     }
-    cudaError_t e = periodic_axes(f, g, s->d.nv, s->d.storage, s->d.vmax, mask, 0, g.n[0], st, &s->launches);
+    if (s->ghost_fresh) mask &= ~s->wrap_mask;   // images were written by the previous fused launch
+    cudaError_t e = periodic_axes(f, g, s->sel, s->d.storage, s->d.vmax, mask, 0, g.n[0], st, &s->launches);
     if (e != cudaSuccess) return set_error(-(int)e, "periodic update", cudaGetErrorString(e));
     return 0;
 }
@@ -627,10 +665,13 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
         s->prof_used += 2;
         cudaEventRecord(ev0, st);
     }
-    rc = s->d.one_time_step(f, fnew, &s->d.grid, scal, (void*)st);
+    lbmk_grid g = s->d.grid;
+    g.wrap = s->wrap_mask;
+    rc = s->d.one_time_step(f, fnew, &g, scal, (void*)st);
     if (rc) return set_error(rc, "one_time_step kernel launch", cudaGetErrorString((cudaError_t)(-rc)));
     if (ev1) cudaEventRecord(ev1, st);
     s->launches += 1;
+    s->ghost_fresh = 1;   // fnew (the next f) now carries its periodic images
     return 0;
 }
 
@@ -638,6 +679,7 @@ static int build_graph(lbm_sim* s) {
     drop_graph(s);
     cudaGraph_t graph = nullptr;
     const int64_t before = s->launches;
+    const int fresh_at_capture = s->ghost_fresh;
     CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     int rc = one_step(s, s->f, s->fnew, s->t, s->stream);
     if (rc == 0) rc = one_step(s, s->fnew, s->f, s->t, s->stream);
@@ -650,6 +692,7 @@ static int build_graph(lbm_sim* s) {
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return set_error(-(int)e, "cudaGraphInstantiate", cudaGetErrorString(e));
     s->graph_f = s->f;
+    s->graph_fresh = fresh_at_capture;
     return 0;
 }
 
@@ -657,8 +700,17 @@ extern "C" int lbm_sim_step(lbm_sim* s, int nsteps) {
     if (!s || nsteps < 0) return ARG_ERROR("lbm_sim_step");
     int done = 0;
     const bool graph_ok = s->use_graph && s->d.t_index < 0 && s->nranks == 1 && !s->profile;
-    if (graph_ok && nsteps >= 2) {
-        if (!s->graph || s->graph_f != s->f) {
+    if (graph_ok && nsteps >= 3 && !s->ghost_fresh && s->wrap_mask) {
+        // first step refreshes the ghosts with the copy kernels; the captured pairs then skip them
+        int rc = one_step(s, s->f, s->fnew, s->t, s->stream);
+        if (rc) return rc;
+        void* tmp = s->f; s->f = s->fnew; s->fnew = tmp;
+        s->t += s->d.dt;
+        s->nt += 1;
+        done = 1;
+    }
+    if (graph_ok && nsteps - done >= 2) {
+        if (!s->graph || s->graph_f != s->f || s->graph_fresh != s->ghost_fresh) {
             int rc = build_graph(s);
             if (rc) return rc;
         }
@@ -705,6 +757,13 @@ extern "C" int lbm_sim_state(lbm_sim* s, void** f, void** fnew, double* t, int64
 extern "C" int lbm_sim_set_state(lbm_sim* s, void* f, void* fnew, double t) {
     if (!s || !f || !fnew) return ARG_ERROR("lbm_sim_set_state");
     s->f = f; s->fnew = fnew; s->t = t;
+    s->ghost_fresh = 0;
+    return 0;
+}
+
+extern "C" int lbm_sim_invalidate_ghosts(lbm_sim* s) {
+    if (!s) return ARG_ERROR("null sim");
+    s->ghost_fresh = 0;
     return 0;
 }
 
@@ -772,5 +831,8 @@ extern "C" int lbm_sim_comm_init(lbm_sim* s, int rank, int nranks, const void* i
     nccl_uid id;
     memcpy(&id, id128, 128);
     NCCL_TRY(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
+    s->wrap_mask &= ~(1 << s->slab_axis);   // the slab axis is exchanged between ranks, not wrapped
+    s->ghost_fresh = 0;
+    drop_graph(s);
     return 0;
 }

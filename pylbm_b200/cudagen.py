@@ -167,6 +167,8 @@ typedef struct {
     int lo[3];         // loop begin per axis
     int hi[3];         // loop end per axis
     int tx;            // threads of a block along the fastest axis (power of two <= block size)
+    int w[3];          // ghost width per axis
+    int wrap;          // bit a set: the fused kernel also writes the periodic images along axis a
     int64_t pitch;     // elements between two consecutive rows of the fastest axis
     int64_t lead;      // position of logical index 0 inside a row
     int64_t pstride;   // elements between two populations
@@ -185,25 +187,28 @@ _KERNEL = r"""
 __global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
 lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g%(scalar_params)s)
 {
-    const int tid = threadIdx.x;
-    const int ty = LBMK_BLOCK / g.tx;
-    const int nchunk = (g.hi[2] - g.lo[2] + g.tx - 1) / g.tx;
-    const long long bid = blockIdx.x;
-    const int chunk = (int)(bid %% nchunk);
-    const long long rowblock = bid / nchunk;
-    const int i2 = g.lo[2] + chunk * g.tx + (tid & (g.tx - 1));
-    const int n1in = g.hi[1] - g.lo[1];
-    const long long row = rowblock * ty + tid / g.tx;
-    const long long nrows = (long long)(g.hi[0] - g.lo[0]) * n1in;
+    const unsigned tid = threadIdx.x;
+    const unsigned tx = (unsigned)g.tx;
+    const unsigned ty = LBMK_BLOCK / tx;
+    const unsigned nchunk = ((unsigned)(g.hi[2] - g.lo[2]) + tx - 1) / tx;
+    const unsigned bid = blockIdx.x;
+    const unsigned rowblock = bid / nchunk;
+    const unsigned chunk = bid - rowblock * nchunk;
+    const int i2 = g.lo[2] + (int)(chunk * tx + (tid & (tx - 1)));
+    const unsigned n1in = (unsigned)(g.hi[1] - g.lo[1]);
+    const unsigned row = rowblock * ty + tid / tx;
+    const unsigned nrows = (unsigned)(g.hi[0] - g.lo[0]) * n1in;
     if (i2 >= g.hi[2] || row >= nrows) return;
-    const int i0 = g.lo[0] + (int)(row / n1in);
-    const int i1 = g.lo[1] + (int)(row %% n1in);
+    const unsigned r0 = row / n1in;
+    const int i0 = g.lo[0] + (int)r0;
+    const int i1 = g.lo[1] + (int)(row - r0 * n1in);
     const long long rowstride = g.pitch;
     const long long planestride = (long long)g.n[1] * g.pitch;
     const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
 %(loads)s
 %(body)s
 %(stores)s
+%(images)s
 }
 
 extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)
@@ -214,12 +219,68 @@ extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, co
     const int ty = LBMK_BLOCK / g->tx;
     const long long nchunk = (n2 + g->tx - 1) / g->tx;
     const long long nblocks = nchunk * ((nrows + ty - 1) / ty);
-    if (nblocks > 2147483647LL) return -2;
+    if (nblocks > 2147483647LL || nrows > 2147483647LL) return -2;
     lbmk_kernel_%(name)s<<<(unsigned)nblocks, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
         (const %(tin)s*)fin, (%(tout)s*)fout, *g%(scalar_args)s);
     return -(int)cudaGetLastError();
 }
 """
+
+
+# Periodic images.  The reference refreshes the ghost layers at the START of every step by copying
+# the opposite interior planes, axis by axis (storage.py:333-367).  Here the ghost values that can
+# ever be read are produced at the END of the previous step instead: a cell within `w` of a face also
+# stores its new populations to its periodic image(s), so no separate copy kernels run.
+# A ghost cell displaced from the interior along the axes A is only ever read -- by the pull of the
+# fused kernel or by a boundary-kernel load (bounce-back/Bouzidi/Neumann read `store + v` style
+# positions) -- for the populations whose velocity points from that ghost cell into the interior along
+# every axis of A.  Only those (population, image) pairs are stored; the other ghost entries are
+# scratch (they are also never refreshed in the reference's Fnew, simulation.py:417).
+_IMAGES_HEAD = r"""    if (g.wrap) {
+        long long d0 = 0, d1 = 0, d2 = 0;   // offset of the image along each axis (0: none)
+        if ((g.wrap & 1) && g.w[0] > 0) {
+            const int nin = g.n[0] - 2 * g.w[0];
+            if (i0 < 2 * g.w[0]) d0 = (long long)nin * planestride; else if (i0 >= nin) d0 = -(long long)nin * planestride;
+        }
+        if ((g.wrap & 2) && g.w[1] > 0) {
+            const int nin = g.n[1] - 2 * g.w[1];
+            if (i1 < 2 * g.w[1]) d1 = (long long)nin * rowstride; else if (i1 >= nin) d1 = -(long long)nin * rowstride;
+        }
+        if ((g.wrap & 4) && g.w[2] > 0) {
+            const int nin = g.n[2] - 2 * g.w[2];
+            if (i2 < 2 * g.w[2]) d2 = nin; else if (i2 >= nin) d2 = -nin;
+        }
+        if (d0 | d1 | d2) {   // rare: only the cells within w of a face
+            // image in the HIGH ghost layer (d > 0) is read by populations moving in -axis, and vice versa
+            const bool p0 = d0 < 0, m0 = d0 > 0, p1 = d1 < 0, m1 = d1 > 0, p2 = d2 < 0, m2 = d2 > 0;
+            (void)p0; (void)m0; (void)p1; (void)m1; (void)p2; (void)m2;
+"""
+
+
+def _images_code(velocities, tout):
+    """tail of the fused kernel: stores of the needed (population, image) pairs."""
+    import itertools
+
+    lines = [_IMAGES_HEAD]
+    dname = ["d0", "d1", "d2"]
+    moving = [k for k, v in enumerate(velocities) if any(c != 0 for c in v)]
+    # re-read this thread's own stores, all loads issued back to back (one memory latency)
+    for k in moving:
+        lines.append("            const %s v%d_ = fout[%dLL * g.pstride + cell];" % (tout, k, k))
+    for k in moving:
+        v = velocities[k]
+        axes = [a for a in range(3) if v[a] != 0]
+        conds = {a: ("p%d" % a if v[a] > 0 else "m%d" % a) for a in axes}
+        lines.append("            { %s* p_ = fout + (%dLL * g.pstride + cell);" % (tout, k))
+        for r in range(1, len(axes) + 1):
+            for sub in itertools.combinations(axes, r):
+                cond = " && ".join(conds[a] for a in sub)
+                off = " + ".join(dname[a] for a in sub)
+                lines.append("              if (%s) p_[%s] = v%d_;" % (cond, off, k))
+        lines.append("            }")
+    lines.append("        }")
+    lines.append("    }")
+    return "\n".join(lines)
 
 
 def _offset_expr(off):
@@ -240,7 +301,7 @@ def _canonical(offset):
     return (0,) * (3 - len(offset)) + offset
 
 
-def kernel_source(ir, storage="double", cse=True, minblocks=1):
+def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False):
     temps, outs = lower_statements(ir.statements, ir.outputs, cse=cse)
     nq = len(ir.in_syms)
     tin = "real_m" if ir.in_array == "m" else "real_f"
@@ -270,6 +331,7 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1):
         scalar_params=scal_params,
         scalar_args=scal_args,
         loads="\n".join(loads),
+        images=_images_code([tuple(-o for o in _canonical(off)) for off in ir.in_offsets], tout) if images else "",
         body="\n".join(body),
         stores="\n".join(stores),
     )
@@ -306,6 +368,17 @@ extern "C" const char* lbmk_describe(void)
 """
 
 
+def default_minblocks(nv):
+    """resident 128-thread blocks per SM requested through __launch_bounds__ for the fused
+    kernel (caps registers: 65536 / (128 * minblocks)); tuned on B200, see DESIGN.md."""
+    import os
+
+    env = os.environ.get("PYLBM_B200_MINBLOCKS")
+    if env:
+        return int(env)
+    return 5
+
+
 def generate_source(kernels, dim, nv, storage="double", cse=True):
     """
     Full translation unit for a list of KernelIR.  Returns (source, info dict).
@@ -315,7 +388,9 @@ def generate_source(kernels, dim, nv, storage="double", cse=True):
     parts = [_HEADER % dict(abi=ABI_VERSION, storage=storage)]
     info = {"abi": ABI_VERSION, "dim": dim, "nv": nv, "storage": storage, "routines": {}}
     for ir in kernels:
-        src, ops = kernel_source(ir, storage=storage, cse=cse)
+        fused = ir.name == "one_time_step"
+        src, ops = kernel_source(ir, storage=storage, cse=cse, images=fused,
+                                 minblocks=default_minblocks(nv) if fused else 1)
         parts.append(src)
         info["routines"][ir.name] = {
             "scalars": list(ir.scalars),

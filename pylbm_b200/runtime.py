@@ -30,6 +30,8 @@ class LbmkGrid(Structure):
         ("lo", c_int * 3),
         ("hi", c_int * 3),
         ("tx", c_int),
+        ("w", c_int * 3),
+        ("wrap", c_int),
         ("pitch", c_int64),
         ("lead", c_int64),
         ("pstride", c_int64),
@@ -59,7 +61,7 @@ class LbmSimDesc(Structure):
         ("scalars", c_double * 32),
         ("t", c_double),
         ("dt", c_double),
-        ("xmask", c_uint8 * 64),
+        ("vel", (ctypes.c_int8 * 3) * 64),
     ]
 
 
@@ -100,6 +102,7 @@ _SIGNATURES = {
     "lbm_sim_sync": (c_int, [c_void_p]),
     "lbm_sim_state": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_double), POINTER(c_int64)]),
     "lbm_sim_set_state": (c_int, [c_void_p, c_void_p, c_void_p, c_double]),
+    "lbm_sim_invalidate_ghosts": (c_int, [c_void_p]),
     "lbm_sim_use_graph": (c_int, [c_void_p, c_int]),
     "lbm_sim_set_overlap": (c_int, [c_void_p, c_int]),
     "lbm_sim_timer_start": (c_int, [c_void_p]),

@@ -220,8 +220,10 @@ class Simulation:
         for i, v in enumerate(values):
             desc.scalars[i] = v
         desc.t, desc.dt = self.t, self.dt
+        vel = self.scheme.stencil.get_all_velocities()
         for k in range(F.nv):
-            desc.xmask[k] = 1
+            for d in range(self.dim):
+                desc.vel[k][3 - self.dim + d] = int(vel[k][d])
         handle = rt.lib().lbm_sim_create(ctypes.byref(desc))
         if not handle:
             raise rt.LbmError("lbm_sim_create failed: %s" % rt.lib().lbm_last_error().decode())
@@ -277,6 +279,7 @@ class Simulation:
         else:
             self.f2m()
         self.container.Fnew.copy_from(self.container.F)
+        self._invalidate_ghosts()
         self._update_m = True
         self.container.release_m()   # rebuilt on demand by f2m; frees nv * cells * 8 bytes of HBM
 
@@ -297,6 +300,11 @@ class Simulation:
         dev.set(host.array.reshape(host.nv, ncell))
         return dev
 
+    def _invalidate_ghosts(self):
+        """F was written from outside the step loop: the next step must refresh its ghost layers."""
+        if self._handle:
+            rt.check(rt.lib().lbm_sim_invalidate_ghosts(self._handle), "lbm_sim_invalidate_ghosts")
+
     def f2m(self, **kwargs):
         self._launch("f2m", self.container.F, self.container.m)
 
@@ -308,6 +316,7 @@ class Simulation:
             f_user.array[...] = df.get().reshape(f_user.array.shape)
             return
         self._launch("m2f", self.container.m, self.container.F)
+        self._invalidate_ghosts()
 
     def equilibrium(self, m_user=None, **kwargs):
         if m_user is not None:
@@ -327,6 +336,7 @@ class Simulation:
         F, Fnew = self.container.F, self.container.Fnew
         self._launch("transport", F, Fnew, inner=True)
         F.copy_from(Fnew)
+        self._invalidate_ghosts()
 
     # ---- item properties (reference: simulation.py:200-243) -----------------
     def _refresh_m(self):
@@ -362,6 +372,7 @@ class Simulation:
         def put(self_, i, value):
             self_._update_m = True
             self_.container.F[i] = value
+            self_._invalidate_ghosts()
 
         return _ItemProperty(self, get, put)
 

@@ -102,6 +102,8 @@ class DeviceArray(_ConsmMixin):
             self.grid.n[a] = n[a]
             self.grid.lo[a] = 0
             self.grid.hi[a] = n[a]
+            self.grid.w[a] = w[a]
+        self.grid.wrap = 0
         tx = 128
         while tx > 1 and tx // 2 >= n[2]:
             tx //= 2
