@@ -200,13 +200,14 @@ void equilibrium(double* mm, int nx, int ny, int nz, double t, double dt, const 
     }
 }
 
-/* periodic ghost update, one rank: dimension by dimension */
-void periodic_update(double* f, int nx, int ny, int nz)
+/* periodic ghost update, one rank: dimension by dimension; skip_axis (or -1) is left to the caller
+   (slab decomposition: that axis is exchanged with the neighbour ranks first) */
+void periodic_update(double* f, int nx, int ny, int nz, int skip_axis)
 {
     const int w[3] = {%(vmax0)d, %(vmax1)d, %(vmax2)d};
     const int n[3] = {nx, ny, nz};
     for (int d = 0; d < 3; ++d) {
-        if (w[d] == 0) continue;
+        if (w[d] == 0 || d == skip_axis) continue;
         for (int ix = 0; ix < nx; ++ix) for (int iy = 0; iy < ny; ++iy) for (int iz = 0; iz < nz; ++iz) {
             int i[3] = {ix, iy, iz};
             int src = -1;
@@ -340,12 +341,16 @@ class OracleSimulation:
     compare: `m[sym]`, `F`, boundary lists `bc.methods`, `one_time_step()`.
     """
 
-    def __init__(self, dico, openmp=False, threads=None):
+    def __init__(self, dico, openmp=False, threads=None, topology=None, exchange=None):
+        """`topology` (pylbm_b200.domain.SlabTopology) + `exchange(array, width)` run this object as
+        one x-slab: `exchange` must fill the x ghost planes of the AoS array from the neighbour
+        ranks (reference: storage.py:333-367 with several ranks); used by the gloo tests."""
         from pylbm_b200.boundary import Boundary
         from pylbm_b200.domain import Domain
         from pylbm_b200.scheme import Scheme
 
-        self.domain = Domain(dico)
+        self.domain = Domain(dico, topology=topology)
+        self.exchange = exchange
         self.scheme = Scheme(dico)
         self.dim = self.domain.dim
         self.lib, self.extra_names = build_library(self.scheme, openmp=openmp)
@@ -435,7 +440,11 @@ class OracleSimulation:
     def boundary_condition(self):
         f = self._F.array
         n = [ctypes.c_int(v) for v in self.n3]
-        self.lib.periodic_update(_ptr(f), *n)
+        if self.exchange is not None:
+            self.exchange(f, int(self.domain.stencil.vmax[0]))
+            self.lib.periodic_update(_ptr(f), *n, ctypes.c_int(0))
+        else:
+            self.lib.periodic_update(_ptr(f), *n, ctypes.c_int(-1))
         for method in self.bc.methods:
             if method.is_time_dependent:
                 method.update_feq(self)

@@ -30,11 +30,28 @@ def _default_mod():
     return pylbm_b200
 
 
+class _Wave(int):
+    """perturb='wave': smooth perturbation that depends on the COORDINATES only (not on the local
+    array shape), so that every slab of a decomposed run initialises the same global field."""
+
+    def __add__(self, other):
+        return _Wave(int(self) + other)
+
+
+WAVE = _Wave(0)
+
+
 def _perturbed(seed, base, amp=0.01):
-    """callable init: base + amp*U(-1,1), one independent stream per moment."""
+    """callable init: base + amp*U(-1,1), one independent stream per moment (seeded NumPy
+    generator over the local array), or a coordinate-based wave for seed = WAVE + i."""
 
     def init(*coords):
         shape = np.broadcast(*coords).shape
+        if isinstance(seed, _Wave):
+            field = np.ones(shape)
+            for i, c in enumerate(coords):
+                field = field * np.cos(2 * np.pi * (2 + i + int(seed)) * c + 0.7 * (i + 1) + int(seed))
+            return base + amp * field
         rng = np.random.default_rng(seed)
         return base + amp * rng.uniform(-1.0, 1.0, size=shape)
 
@@ -103,7 +120,8 @@ def lid_cavity_d2q9(n=256, mod=None, perturb=None, generator="cuda"):
     }
 
 
-def karman_d2q9(nx=4096, ny=1024, mod=None, perturb=None, generator="cuda", relative_velocity=True):
+def karman_d2q9(nx=4096, ny=1024, mod=None, perturb=None, generator="cuda", relative_velocity=True,
+                radius=1.0 / 16, cx=None):
     """C2: D2Q9 Karman vortex street nx x ny behind a circular obstacle (Bouzidi bounce-back
     on inlet, walls and obstacle, Neumann outlet)."""
     mod = mod or _default_mod()
@@ -120,7 +138,7 @@ def karman_d2q9(nx=4096, ny=1024, mod=None, perturb=None, generator="cuda", rela
         }
     dico = {
         "box": {"x": [0.0, length], "y": [0.0, 1.0], "label": [0, 1, 0, 0]},
-        "elements": [mod.Circle([0.15 * length, 0.5 + 2 * dx], 1.0 / 16, label=2)],
+        "elements": [mod.Circle([0.15 * length if cx is None else cx, 0.5 + 2 * dx], radius, label=2)],
         "space_step": dx,
         "scheme_velocity": la,
         "schemes": [

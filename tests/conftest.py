@@ -13,6 +13,10 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def case_id(name, kw):
+    return name + "-" + "x".join(str(v) for v in kw.values())
+
+
 @pytest.fixture(scope="session")
 def small_cases():
     """(name, kwargs) of the parity workloads at sizes the oracle finishes in seconds."""

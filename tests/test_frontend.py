@@ -1,0 +1,132 @@
+"""Host front-end: velocity numbering, lean sparse domain, boundary-list scheduling."""
+import numpy as np
+import pytest
+
+
+def test_velocity_numbering_convention():
+    from pylbm_b200.stencil import Velocity
+
+    # reference convention (pylbm/stencil.py:285-373): D1, D2Q9 shell, D3Q19/27 order
+    assert [Velocity(dim=1, num=i).v for i in range(5)] == [[0], [1], [-1], [2], [-2]]
+    d2 = [(0, 0), (1, 0), (0, 1), (-1, 0), (0, -1), (1, 1), (-1, 1), (-1, -1), (1, -1)]
+    assert [tuple(Velocity(dim=2, num=i).v) for i in range(9)] == d2
+    assert tuple(Velocity(dim=2, num=9).v) == (2, 0) and tuple(Velocity(dim=2, num=17).v) == (2, 1)
+    d3 = [(0, 0, 0), (0, 0, 1), (0, 0, -1), (0, 1, 0), (0, -1, 0), (1, 0, 0), (-1, 0, 0),
+          (0, 1, 1), (0, 1, -1), (0, -1, 1), (0, -1, -1), (1, 0, 1), (1, 0, -1), (-1, 0, 1), (-1, 0, -1),
+          (1, 1, 0), (1, -1, 0), (-1, 1, 0), (-1, -1, 0), (1, 1, 1)]
+    assert [tuple(Velocity(dim=3, num=i).v) for i in range(20)] == d3
+    for dim, count in ((1, 30), (2, 120), (3, 200)):
+        for num in range(count):
+            v = Velocity(dim=dim, num=num)
+            full = v.v + [None] * (3 - dim)
+            assert Velocity(vx=full[0], vy=full[1], vz=full[2]).num == num
+            assert v.get_symmetric().get_symmetric().num == num
+
+
+def test_stencil_symmetric_index_per_scheme():
+    from pylbm_b200.stencil import Stencil
+
+    st = Stencil({"box": {"x": [0, 1], "y": [0, 1]},
+                  "schemes": [{"velocities": list(range(1, 5))}, {"velocities": [0, 5, 6, 7, 8, 1, 3, 2, 4]}]})
+    vel = st.get_all_velocities()
+    ksym = st.get_symmetric()
+    assert np.array_equal(vel[ksym], -vel)
+    assert list(st.nv_ptr) == [0, 4, 13] and st.unvtot == 9 and list(st.vmax) == [1, 1]
+    assert np.array_equal(vel[st.get_symmetric(axis=0)][:, 0], vel[:, 0])
+
+
+def test_lean_domain_matches_dense_semantics():
+    import pylbm_b200 as lb
+
+    dico = {"box": {"x": [0, 2], "y": [0, 1], "label": [0, 1, 0, -1]},
+            "elements": [lb.Circle([0.5, 0.5], 0.2, label=2), lb.Parallelogram([1.2, 0.2], [0.3, 0.0], [0.0, 0.4], label=3)],
+            "space_step": 1 / 32, "schemes": [{"velocities": list(range(9))}]}
+    dom = lb.Domain(dico)
+    assert dom.shape_halo == [66, 34] and dom.shape_in == [64, 32]
+    flag, dist = dom.flag, dom.distance
+    ioo = dom.in_or_out
+    # records only on fluid cells, distances in (0, 1]
+    for k in range(dom.stencil.unvtot):
+        touched = flag[k] != dom.valin
+        assert np.all(ioo[touched] == dom.valin)
+        assert np.all((dist[k][touched] > 0) & (dist[k][touched] <= 1))
+    # a link is cut exactly when the neighbour cell is solid / outside (periodic faces carry label -1)
+    vel = dom.stencil.uvel
+    for k in range(1, 9):
+        cut = flag[k][1:-1, 1:-1] != dom.valin
+        nb = ioo[1 + vel[k][0]: 65 + vel[k][0], 1 + vel[k][1]: 33 + vel[k][1]] == dom.valout
+        fluid = ioo[1:-1, 1:-1] == dom.valin
+        assert np.array_equal(cut, nb & fluid)
+    # sparse query == np.where on the dense view, in C order
+    for label in (0, 1, 2, 3):
+        for k in range(9):
+            cells, d = dom.cells_with_flag(k, label)
+            ref = np.where(flag[k] == label)
+            assert all(np.array_equal(a, b) for a, b in zip(cells, ref))
+            assert np.array_equal(d, dist[k][ref])
+
+
+def test_slab_topology_regions_and_interface_labels():
+    import pylbm_b200 as lb
+    from pylbm_b200.domain import SlabTopology
+
+    dico = {"box": {"x": [0, 1], "y": [0, 1], "label": [0, 1, 2, 3]}, "space_step": 1 / 10,
+            "schemes": [{"velocities": list(range(9))}]}
+    regions = [SlabTopology(2, r, 3).get_region(10, 10) for r in range(3)]
+    assert [r[0] for r in regions] == [[0, 4], [4, 7], [7, 10]]     # n // P + (n % P > i), reference mpi_topology.py:82-105
+    doms = [lb.Domain(dico, topology=SlabTopology(2, r, 3)) for r in range(3)]
+    assert doms[0].box_label == [0, -2, 2, 3] and doms[1].box_label == [-2, -2, 2, 3] and doms[2].box_label == [-2, 1, 2, 3]
+    full = lb.Domain(dico)
+    x = np.concatenate([d.coords[0] for d in doms])
+    np.testing.assert_allclose(x, full.coords[0], rtol=0, atol=1e-15)
+
+
+def test_schedule_levels_reproduce_sequential_semantics():
+    from pylbm_b200.boundary import schedule
+
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n = int(rng.integers(1, 40))
+        npos = int(rng.integers(4, 30))
+        store = rng.integers(0, npos, size=n)
+        l0 = rng.integers(0, npos, size=n)
+        l1 = rng.integers(0, npos, size=n)
+        snapshot = bool(trial % 2)
+        f0 = rng.uniform(size=npos)
+        # sequential reference loop
+        f = f0.copy()
+        src = f0.copy() if snapshot else f
+        for i in range(n):
+            f[store[i]] = 0.25 * src[l0[i]] + 0.5 * src[l1[i]] + i
+        # levelled execution
+        order, ptr, two = schedule(store, [l0, l1], snapshot=snapshot)
+        g = f0.copy()
+        idx = np.arange(n)[order]
+        for lev in range(len(ptr) - 1):
+            sel = idx[ptr[lev]: ptr[lev + 1]]
+            base = f0 if snapshot else g
+            if two[lev]:
+                vals = 0.25 * base[l0[sel]] + 0.5 * base[l1[sel]] + sel
+                g[store[sel]] = vals
+            else:   # in place, any order inside the level must give the same result
+                for i in sel[::-1]:
+                    g[store[i]] = 0.25 * base[l0[i]] + 0.5 * base[l1[i]] + i
+        assert np.array_equal(f, g), trial
+
+
+def test_boundary_lists_without_aliasing_are_single_level():
+    import pylbm_b200 as lb
+    from pylbm_b200 import cases
+    from pylbm_b200.boundary import Boundary, schedule
+
+    dico = cases.lid_cavity_d3q19(n=12)
+    dom = lb.Domain(dico)
+    bc = Boundary(dom, None, dico)
+    (method,) = bc.methods
+    method.set_iload()
+    method.fix_iload()
+    shape = dom.shape_halo
+    pos = lambda a: np.ravel_multi_index((a[:, 0], a[:, 1], a[:, 2], a[:, 3]), [19] + shape)
+    order, ptr, two = schedule(pos(method.istore), [pos(method.iload[0])])
+    assert len(ptr) == 2 and not two[0] and np.array_equal(order, np.arange(order.size))
+    assert method.istore.shape == (6 * 12 * 12 * 5 - 0, 4) or method.istore.shape[1] == 4
