@@ -204,7 +204,8 @@ def main():
     ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--no-overlap", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU halo: direct NVLink peer stores from the fused kernel, or NCCL send/recv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -264,9 +265,14 @@ def main():
 
     dico = cases.CASES[case_name](**case_kw)
     t_build = time.time()
-    sim = pylbm_b200.Simulation(dico, dtype=args.dtype, slab=(rank, world) if world > 1 else None, nccl_id=nccl_id)
-    if world > 1 and not args.no_overlap:
-        lib.lbm_sim_set_overlap(sim._handle, 1)
+    gather = None
+    if world > 1 and args.halo == "peer":
+        def gather(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+    sim = pylbm_b200.Simulation(dico, dtype=args.dtype, slab=(rank, world) if world > 1 else None, nccl_id=nccl_id,
+                                gather=gather)
     t_build = time.time() - t_build
     global_cells = float(np.prod(sim.domain.global_size))
     local_cells = float(np.prod(sim.domain.shape_in))
@@ -368,7 +374,8 @@ def main():
             "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32-storage/f64-math",
-            "data": "synthetic", "config": dict(config, parallelism="x-slabs x%d" % world, setup_s=round(t_build, 2)),
+            "data": "synthetic", "config": dict(config, parallelism="x-slabs x%d" % world, setup_s=round(t_build, 2),
+                           halo=(args.halo if world > 1 else "periodic (single GPU)")),
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),
             "clocks": clocks, "frac_of_roofline": value / (world * roofline["roofline_mlups_per_gpu"]),
         }

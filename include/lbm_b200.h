@@ -100,6 +100,7 @@ typedef struct {
     void* f;                /* device arrays (caller-owned)                              */
     void* fnew;
     lbmk_launch_fn one_time_step;  /* from the generated kernel library                  */
+    lbmk_launch_peers_fn one_time_step_peers;   /* same, with peer stores (may be NULL)  */
     int nscalars;           /* runtime scalars of the fused kernel                       */
     int t_index;            /* position of `t` in scalars[], or -1                       */
     double scalars[32];
@@ -155,6 +156,15 @@ void* lbm_sim_stream(lbm_sim* sim);
 /* ---- multi-GPU: x-slabs, one process per GPU, NCCL send/recv over NVLink ---- */
 int lbm_comm_unique_id(void* id128);   /* 128-byte ncclUniqueId, created on rank 0 */
 int lbm_sim_comm_init(lbm_sim* sim, int rank, int nranks, const void* id128);
+
+/* Direct NVLink halo: every rank exports CUDA-IPC handles of its two population arrays and of a
+ * small flag buffer (lbm_sim_ipc_export: 3 x 64 bytes + geometry), gathers the blobs of its two ring
+ * neighbours by any means (torch.distributed, a queue, ...) and opens them (lbm_sim_ipc_open).
+ * From then on the fused kernel stores the slab-face images straight into the neighbours' ghost
+ * planes and the ranks synchronise with device-side arrival counters: no NCCL call per step. */
+#define LBM_IPC_BLOB_BYTES 256
+int lbm_sim_ipc_export(lbm_sim* sim, void* blob256);
+int lbm_sim_ipc_open(lbm_sim* sim, const void* left_blob256, const void* right_blob256);
 
 #ifdef __cplusplus
 }

@@ -47,6 +47,20 @@ typedef struct {
     int64_t pstride;  /* elements between consecutive populations                    */
 } lbmk_grid;
 
+/*
+ * Neighbour slabs of a multi-GPU run (one process per GPU, x-slabs).  When given, the fused kernel
+ * stores the populations leaving through its low / high slab face DIRECTLY into the ghost planes of
+ * the neighbour rank's array (peer-mapped with CUDA IPC, NVLink) -- the per-step halo exchange of
+ * the reference (mpi4py Isend/Irecv, storage.py:333-367) fused into the compute kernel.
+ */
+typedef struct {
+    void* lo;            /* neighbour array receiving the images of my LOW-face cells (its high ghost) */
+    void* hi;            /* neighbour array receiving the images of my HIGH-face cells (its low ghost) */
+    int64_t pstride_lo;  /* population stride of those arrays                                          */
+    int64_t pstride_hi;
+    int nin_lo;          /* interior size of the `lo` neighbour along the slab axis                    */
+} lbmk_peers;
+
 /* ABI version the library was generated for. */
 int lbmk_abi_version(void);
 
@@ -66,6 +80,11 @@ typedef int (*lbmk_launch_fn)(const void* fin, void* fout, const lbmk_grid* g,
                               const double* scalars, void* stream);
 
 int lbmk_one_time_step(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+/* same with direct peer stores of the slab-face images (peers may be NULL) */
+typedef int (*lbmk_launch_peers_fn)(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                                    const lbmk_peers* peers, void* stream);
+int lbmk_one_time_step_peers(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                             const lbmk_peers* peers, void* stream);
 int lbmk_transport(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_f2m(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_m2f(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);

@@ -394,6 +394,31 @@ extern "C" int lbm_comm_unique_id(void* id128) {
 }
 
 // ---------------------------------------------------------------------------
+// device-side synchronisation between neighbour ranks (direct NVLink halo)
+// ---------------------------------------------------------------------------
+// After its fused kernel of step s a rank increments an arrival counter in each neighbour's memory;
+// before touching the ghost planes of step s+1 it waits until both neighbours have arrived s+1 times.
+// Counters only grow and the expected value lives on the device, so the same two kernels can be
+// replayed from a CUDA graph.
+__global__ void k_signal(unsigned long long* to_left, unsigned long long* to_right) {
+    __threadfence_system();
+    if (threadIdx.x == 0) atomicAdd_system(to_left, 1ULL);    // I am the RIGHT neighbour of my left rank
+    if (threadIdx.x == 1) atomicAdd_system(to_right, 1ULL);   // and the LEFT neighbour of my right rank
+}
+
+__global__ void k_wait(unsigned long long* flags) {
+    // flags[0], flags[1]: arrivals from the left / right neighbour; flags[2], flags[3]: my epochs
+    const int i = threadIdx.x;
+    if (i < 2) {
+        const unsigned long long want = flags[2 + i] + 1ULL;
+        volatile unsigned long long* arr = flags + i;
+        while (*arr < want) { __nanosleep(100); }
+        flags[2 + i] = want;
+    }
+    __threadfence_system();
+}
+
+// ---------------------------------------------------------------------------
 // time-step object
 // ---------------------------------------------------------------------------
 struct BcMethod {
@@ -421,6 +446,15 @@ struct lbm_sim {
     int rank = 0, nranks = 1;
     int slab_axis = 0;
     int overlap = 0;
+    // direct NVLink halo (CUDA IPC): peer arrays [side lo/hi][buffer A/B], arrival counters
+    int peers_ready = 0;
+    long long signals = 0, waits = 0;             // enqueued so far (host-side bookkeeping)
+    void* buf[2] = {nullptr, nullptr};            // my arrays A (= desc.f) and B (= desc.fnew)
+    void* peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    long long peer_pstride[2] = {0, 0};
+    int peer_nin_lo = 0;
+    unsigned long long* flags = nullptr;          // [0],[1]: arrivals from left/right; [2],[3]: my epochs
+    unsigned long long* peer_flags[2] = {nullptr, nullptr};
     // CUDA graph of two consecutive steps (f->fnew, fnew->f)
     int use_graph = 0;
     cudaGraphExec_t graph = nullptr;
@@ -450,6 +484,8 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
     s->d = *desc;
     s->f = desc->f;
     s->fnew = desc->fnew;
+    s->buf[0] = desc->f;
+    s->buf[1] = desc->fnew;
     s->t = desc->t;
     // slab axis = first real axis of the canonical 3-D grid
     s->slab_axis = 0;
@@ -633,8 +669,23 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
     const lbmk_grid& g = s->d.grid;
     int mask = s->d.periodic_mask;
     if (s->nranks > 1) {
-        int rc = exchange_slabs(s, f, st);
-        if (rc) return rc;
+        if (s->peers_ready && s->ghost_fresh) {
+            // the neighbours stored their slab-face images into my ghost planes during their previous
+            // fused kernel: just wait for both of them to have finished it
+            k_wait<<<1, 32, 0, st>>>(s->flags);
+            s->launches += 1;
+            s->waits += 1;
+        } else {
+            int rc = exchange_slabs(s, f, st);
+            if (rc) return rc;
+            if (s->peers_ready && s->waits < s->signals) {
+                // a signal of the previous step is still pending (the ghosts were invalidated from
+                // outside): consume it so that the arrival counters stay in step
+                k_wait<<<1, 32, 0, st>>>(s->flags);
+                s->launches += 1;
+                s->waits += 1;
+            }
+        }
         mask &= ~(1 << s->slab_axis);
     }
     if (s->ghost_fresh) mask &= ~s->wrap_mask;   // images were written by the previous fused launch
@@ -667,10 +718,26 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
     }
     lbmk_grid g = s->d.grid;
     g.wrap = s->wrap_mask;
-    rc = s->d.one_time_step(f, fnew, &g, scal, (void*)st);
+    if (s->peers_ready) {
+        const int which = (fnew == s->buf[0]) ? 0 : 1;   // all ranks swap A/B in lockstep
+        lbmk_peers pr;
+        pr.lo = s->peer_buf[0][which];
+        pr.hi = s->peer_buf[1][which];
+        pr.pstride_lo = s->peer_pstride[0];
+        pr.pstride_hi = s->peer_pstride[1];
+        pr.nin_lo = s->peer_nin_lo;
+        rc = s->d.one_time_step_peers(f, fnew, &g, scal, &pr, (void*)st);
+    } else {
+        rc = s->d.one_time_step(f, fnew, &g, scal, (void*)st);
+    }
     if (rc) return set_error(rc, "one_time_step kernel launch", cudaGetErrorString((cudaError_t)(-rc)));
     if (ev1) cudaEventRecord(ev1, st);
     s->launches += 1;
+    if (s->peers_ready) {
+        k_signal<<<1, 32, 0, st>>>(s->peer_flags[0] + 1, s->peer_flags[1] + 0);
+        s->launches += 1;
+        s->signals += 1;
+    }
     s->ghost_fresh = 1;   // fnew (the next f) now carries its periodic images
     return 0;
 }
@@ -699,7 +766,7 @@ static int build_graph(lbm_sim* s) {
 extern "C" int lbm_sim_step(lbm_sim* s, int nsteps) {
     if (!s || nsteps < 0) return ARG_ERROR("lbm_sim_step");
     int done = 0;
-    const bool graph_ok = s->use_graph && s->d.t_index < 0 && s->nranks == 1 && !s->profile;
+    const bool graph_ok = s->use_graph && s->d.t_index < 0 && (s->nranks == 1 || s->peers_ready) && !s->profile;
     if (graph_ok && nsteps >= 3 && !s->ghost_fresh && s->wrap_mask) {
         // first step refreshes the ghosts with the copy kernels; the captured pairs then skip them
         int rc = one_step(s, s->f, s->fnew, s->t, s->stream);
@@ -819,6 +886,60 @@ extern "C" int lbm_sim_profile_read(lbm_sim* s, double* fused_ms, int64_t* nlaun
 
 extern "C" int64_t lbm_sim_launch_count(lbm_sim* s) { return s ? s->launches : 0; }
 extern "C" void* lbm_sim_stream(lbm_sim* s) { return s ? (void*)s->stream : nullptr; }
+
+struct IpcBlob {
+    cudaIpcMemHandle_t buf[2];
+    cudaIpcMemHandle_t flags;
+    long long pstride;
+    int nin;
+    int pad;
+};
+static_assert(sizeof(IpcBlob) <= LBM_IPC_BLOB_BYTES, "IPC blob too large");
+
+extern "C" int lbm_sim_ipc_export(lbm_sim* s, void* blob256) {
+    if (!s || !blob256) return ARG_ERROR("lbm_sim_ipc_export");
+    if (!s->flags) {
+        CUDA_TRY(cudaMalloc(&s->flags, 4 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(s->flags, 0, 4 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    IpcBlob b;
+    memset(&b, 0, sizeof(b));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.buf[0], s->buf[0]));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.buf[1], s->buf[1]));
+    CUDA_TRY(cudaIpcGetMemHandle(&b.flags, s->flags));
+    b.pstride = s->d.grid.pstride;
+    b.nin = s->d.grid.n[s->slab_axis] - 2 * s->d.vmax[s->slab_axis];
+    memset(blob256, 0, LBM_IPC_BLOB_BYTES);
+    memcpy(blob256, &b, sizeof(b));
+    return 0;
+}
+
+extern "C" int lbm_sim_ipc_open(lbm_sim* s, const void* left_blob, const void* right_blob) {
+    if (!s || !left_blob || !right_blob) return ARG_ERROR("lbm_sim_ipc_open");
+    if (!s->d.one_time_step_peers) return ARG_ERROR("the kernel library has no lbmk_one_time_step_peers");
+    if (s->nranks < 2 || !s->flags) return ARG_ERROR("lbm_sim_ipc_open needs lbm_sim_comm_init and lbm_sim_ipc_export first");
+    const void* blobs[2] = {left_blob, right_blob};
+    const bool same = (s->nranks == 2);   // both neighbours are the same process: open its handles once
+    for (int side = 0; side < 2; ++side) {
+        IpcBlob b;
+        memcpy(&b, blobs[side], sizeof(b));
+        if (side == 1 && same) {
+            for (int i = 0; i < 2; ++i) s->peer_buf[1][i] = s->peer_buf[0][i];
+            s->peer_flags[1] = s->peer_flags[0];
+        } else {
+            for (int i = 0; i < 2; ++i)
+                CUDA_TRY(cudaIpcOpenMemHandle(&s->peer_buf[side][i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
+            CUDA_TRY(cudaIpcOpenMemHandle((void**)&s->peer_flags[side], b.flags, cudaIpcMemLazyEnablePeerAccess));
+        }
+        s->peer_pstride[side] = b.pstride;
+        if (side == 0) s->peer_nin_lo = b.nin;
+    }
+    s->peers_ready = 1;
+    s->ghost_fresh = 0;
+    drop_graph(s);
+    return 0;
+}
 
 extern "C" int lbm_sim_comm_init(lbm_sim* s, int rank, int nranks, const void* id128) {
     if (!s || nranks < 1 || rank < 0 || rank >= nranks) return ARG_ERROR("lbm_sim_comm_init");

@@ -173,7 +173,15 @@ typedef struct {
     int64_t lead;      // position of logical index 0 inside a row
     int64_t pstride;   // elements between two populations
 } lbmk_grid;
+typedef struct {
+    void* lo;            // neighbour array receiving the images of my LOW-face cells (its high ghost)
+    void* hi;            // neighbour array receiving the images of my HIGH-face cells (its low ghost)
+    int64_t pstride_lo;  // population stride of those arrays
+    int64_t pstride_hi;
+    int nin_lo;          // interior size of the `lo` neighbour along the slab axis
+} lbmk_peers;
 }
+#define SLAB %(slab)d
 
 typedef %(storage)s real_f;   // storage type of the populations in HBM
 typedef double real_m;        // moments are always stored in fp64
@@ -185,7 +193,7 @@ _KERNEL = r"""
 // %(name)s : %(nin)d loads, %(nout)d stores per cell; %(ops)s
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
-lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g%(scalar_params)s)
+lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g%(peer_param)s%(scalar_params)s)
 {
     const unsigned tid = threadIdx.x;
     const unsigned tx = (unsigned)g.tx;
@@ -211,7 +219,7 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
 %(images)s
 }
 
-extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)
+%(launch_head)s
 {
     const long long nrows = (long long)(g->hi[0] - g->lo[0]) * (g->hi[1] - g->lo[1]);
     const int n2 = g->hi[2] - g->lo[2];
@@ -221,10 +229,10 @@ extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, co
     const long long nblocks = nchunk * ((nrows + ty - 1) / ty);
     if (nblocks > 2147483647LL || nrows > 2147483647LL) return -2;
     lbmk_kernel_%(name)s<<<(unsigned)nblocks, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
-        (const %(tin)s*)fin, (%(tout)s*)fout, *g%(scalar_args)s);
+        (const %(tin)s*)fin, (%(tout)s*)fout, *g%(peer_arg)s%(scalar_args)s);
     return -(int)cudaGetLastError();
 }
-"""
+%(launch_tail)s"""
 
 
 # Periodic images.  The reference refreshes the ghost layers at the START of every step by copying
@@ -236,32 +244,42 @@ extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, co
 # positions) -- for the populations whose velocity points from that ghost cell into the interior along
 # every axis of A.  Only those (population, image) pairs are stored; the other ghost entries are
 # scratch (they are also never refreshed in the reference's Fnew, simulation.py:417).
-_IMAGES_HEAD = r"""    if (g.wrap) {
-        long long d0 = 0, d1 = 0, d2 = 0;   // offset of the image along each axis (0: none)
-        if ((g.wrap & 1) && g.w[0] > 0) {
-            const int nin = g.n[0] - 2 * g.w[0];
-            if (i0 < 2 * g.w[0]) d0 = (long long)nin * planestride; else if (i0 >= nin) d0 = -(long long)nin * planestride;
+_IMAGES_HEAD = r"""    if (g.wrap | (pr.lo != nullptr)) {
+        // offset of the image along each axis (0: none).  SLAB is the axis cut into slabs when several
+        // GPUs share the lattice: images across it are stored straight into the neighbour rank's
+        // ghost planes through its peer-mapped array (NVLink), see lbmk_peers.
+        long long d0 = 0, d1 = 0, d2 = 0;
+        %(tout)s* qbase = fout;          // array receiving the images that cross the SLAB axis
+        long long qps = g.pstride;
+        const long long stride_[3] = {planestride, rowstride, 1};
+        const int idx_[3] = {i0, i1, i2};
+        long long d_[3] = {0, 0, 0};
+#pragma unroll
+        for (int a_ = 0; a_ < 3; ++a_) {
+            const bool peer_ = (a_ == SLAB) && pr.lo != nullptr;
+            if (!(((g.wrap >> a_) & 1) || peer_) || g.w[a_] <= 0) continue;
+            const int nin = g.n[a_] - 2 * g.w[a_];
+            if (idx_[a_] < 2 * g.w[a_]) {            // near the low face: image in a HIGH ghost layer
+                d_[a_] = (long long)(peer_ ? pr.nin_lo : nin) * stride_[a_];
+                if (peer_) { qbase = (%(tout)s*)pr.lo; qps = pr.pstride_lo; }
+            } else if (idx_[a_] >= nin) {            // near the high face: image in a LOW ghost layer
+                d_[a_] = -(long long)nin * stride_[a_];
+                if (peer_) { qbase = (%(tout)s*)pr.hi; qps = pr.pstride_hi; }
+            }
         }
-        if ((g.wrap & 2) && g.w[1] > 0) {
-            const int nin = g.n[1] - 2 * g.w[1];
-            if (i1 < 2 * g.w[1]) d1 = (long long)nin * rowstride; else if (i1 >= nin) d1 = -(long long)nin * rowstride;
-        }
-        if ((g.wrap & 4) && g.w[2] > 0) {
-            const int nin = g.n[2] - 2 * g.w[2];
-            if (i2 < 2 * g.w[2]) d2 = nin; else if (i2 >= nin) d2 = -nin;
-        }
+        d0 = d_[0]; d1 = d_[1]; d2 = d_[2];
         if (d0 | d1 | d2) {   // rare: only the cells within w of a face
-            // image in the HIGH ghost layer (d > 0) is read by populations moving in -axis, and vice versa
+            // an image in a HIGH ghost layer (d > 0) is read by populations moving in -axis, and vice versa
             const bool p0 = d0 < 0, m0 = d0 > 0, p1 = d1 < 0, m1 = d1 > 0, p2 = d2 < 0, m2 = d2 > 0;
             (void)p0; (void)m0; (void)p1; (void)m1; (void)p2; (void)m2;
 """
 
 
-def _images_code(velocities, tout):
+def _images_code(velocities, tout, slab):
     """tail of the fused kernel: stores of the needed (population, image) pairs."""
     import itertools
 
-    lines = [_IMAGES_HEAD]
+    lines = [_IMAGES_HEAD % dict(tout=tout)]
     dname = ["d0", "d1", "d2"]
     moving = [k for k, v in enumerate(velocities) if any(c != 0 for c in v)]
     # re-read this thread's own stores, all loads issued back to back (one memory latency)
@@ -271,13 +289,15 @@ def _images_code(velocities, tout):
         v = velocities[k]
         axes = [a for a in range(3) if v[a] != 0]
         conds = {a: ("p%d" % a if v[a] > 0 else "m%d" % a) for a in axes}
-        lines.append("            { %s* p_ = fout + (%dLL * g.pstride + cell);" % (tout, k))
         for r in range(1, len(axes) + 1):
             for sub in itertools.combinations(axes, r):
                 cond = " && ".join(conds[a] for a in sub)
                 off = " + ".join(dname[a] for a in sub)
-                lines.append("              if (%s) p_[%s] = v%d_;" % (cond, off, k))
-        lines.append("            }")
+                if slab in sub:
+                    target = "qbase[%dLL * qps + cell + %s]" % (k, off)
+                else:
+                    target = "fout[%dLL * g.pstride + cell + %s]" % (k, off)
+                lines.append("            if (%s) %s = v%d_;" % (cond, target, k))
     lines.append("        }")
     lines.append("    }")
     return "\n".join(lines)
@@ -301,7 +321,18 @@ def _canonical(offset):
     return (0,) * (3 - len(offset)) + offset
 
 
-def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False):
+_LAUNCH_HEAD = 'extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)'
+_LAUNCH_HEAD_PEERS = ('extern "C" int lbmk_%(name)s_peers(const void* fin, void* fout, const lbmk_grid* g, '
+                      'const double* scalars, const lbmk_peers* peers, void* stream)')
+_LAUNCH_TAIL_PEERS = """
+extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)
+{
+    return lbmk_%(name)s_peers(fin, fout, g, scalars, nullptr, stream);
+}
+"""
+
+
+def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0):
     temps, outs = lower_statements(ir.statements, ir.outputs, cse=cse)
     nq = len(ir.in_syms)
     tin = "real_m" if ir.in_array == "m" else "real_f"
@@ -331,7 +362,11 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False):
         scalar_params=scal_params,
         scalar_args=scal_args,
         loads="\n".join(loads),
-        images=_images_code([tuple(-o for o in _canonical(off)) for off in ir.in_offsets], tout) if images else "",
+        images=_images_code([tuple(-o for o in _canonical(off)) for off in ir.in_offsets], tout, slab) if images else "",
+        peer_param=", const lbmk_peers pr" if images else "",
+        peer_arg=", (peers ? *peers : lbmk_peers{nullptr, nullptr, 0, 0, 0})" if images else "",
+        launch_head=(_LAUNCH_HEAD_PEERS if images else _LAUNCH_HEAD) % dict(name=ir.name),
+        launch_tail=(_LAUNCH_TAIL_PEERS % dict(name=ir.name)) if images else "",
         body="\n".join(body),
         stores="\n".join(stores),
     )
@@ -385,12 +420,12 @@ def generate_source(kernels, dim, nv, storage="double", cse=True):
     """
     import json
 
-    parts = [_HEADER % dict(abi=ABI_VERSION, storage=storage)]
+    parts = [_HEADER % dict(abi=ABI_VERSION, storage=storage, slab=3 - dim)]
     info = {"abi": ABI_VERSION, "dim": dim, "nv": nv, "storage": storage, "routines": {}}
     for ir in kernels:
         fused = ir.name == "one_time_step"
         src, ops = kernel_source(ir, storage=storage, cse=cse, images=fused,
-                                 minblocks=default_minblocks(nv) if fused else 1)
+                                 minblocks=default_minblocks(nv) if fused else 1, slab=3 - dim)
         parts.append(src)
         info["routines"][ir.name] = {
             "scalars": list(ir.scalars),

@@ -56,6 +56,7 @@ class LbmSimDesc(Structure):
         ("f", c_void_p),
         ("fnew", c_void_p),
         ("one_time_step", c_void_p),
+        ("one_time_step_peers", c_void_p),
         ("nscalars", c_int),
         ("t_index", c_int),
         ("scalars", c_double * 32),
@@ -113,6 +114,8 @@ _SIGNATURES = {
     "lbm_sim_stream": (c_void_p, [c_void_p]),
     "lbm_comm_unique_id": (c_int, [c_void_p]),
     "lbm_sim_comm_init": (c_int, [c_void_p, c_int, c_int, c_void_p]),
+    "lbm_sim_ipc_export": (c_int, [c_void_p, c_void_p]),
+    "lbm_sim_ipc_open": (c_int, [c_void_p, c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -172,6 +175,9 @@ class KernelLibrary:
         return self.info["routines"][name]["scalars"]
 
     def address(self, name):
+        if name not in self.routines:
+            fn = getattr(self.handle, "lbmk_" + name)
+            return ctypes.cast(fn, c_void_p).value
         return ctypes.cast(self.routines[name], c_void_p).value
 
     def launch(self, name, fin, fout, grid, scalars=(), stream=None):

@@ -109,11 +109,14 @@ class Simulation:
     codegen_option, lbm_algorithm, show_code).  `dtype='float32'` selects fp32 STORAGE of
     the populations (arithmetic stays fp64) -- new functionality, the reference ignores
     its dtype argument (simulation.py:89-91, storage.py:67).
-    `slab=(rank, nranks)` + `nccl_id` run this process as one x-slab of a multi-GPU run.
+    `slab=(rank, nranks)` + `nccl_id` run this process as one x-slab of a multi-GPU run (NCCL
+    send/recv halo).  `gather(bytes) -> [bytes of every rank]` (an all-gather provided by the caller,
+    e.g. torch.distributed.all_gather_object) additionally enables the direct NVLink halo: the fused
+    kernel stores the slab-face populations straight into the neighbours' ghost planes.
     """
 
     def __init__(self, dico, sorder=None, dtype="float64", check_inverse=False, initialize=True,
-                 slab=None, nccl_id=None):
+                 slab=None, nccl_id=None, gather=None):
         generator = str(dico.get("generator", "cuda")).upper()
         if generator != "CUDA":
             raise ValueError(
@@ -169,6 +172,7 @@ class Simulation:
         self.init_type = dico.get("inittype", "moments")
         self.init_data = dico.get("init", None)
         self._nccl_id = nccl_id
+        self._gather = gather
         self._need_init = True
         if initialize:
             self._initialize()
@@ -210,6 +214,7 @@ class Simulation:
         desc.periodic_mask = sum(1 << a for a in range(3) if F.canonical_vmax[a] > 0)
         desc.f, desc.fnew = F.ptr, Fnew.ptr
         desc.one_time_step = self.kernels.address("one_time_step")
+        desc.one_time_step_peers = self.kernels.address("one_time_step_peers")
         names = self.kernels.scalars("one_time_step")
         desc.nscalars = len(names)
         desc.t_index = names.index("t") if "t" in names else -1
@@ -230,6 +235,14 @@ class Simulation:
         self._handle = handle
         if self.nranks > 1:
             rt.check(rt.lib().lbm_sim_comm_init(handle, self.rank, self.nranks, self._nccl_id), "lbm_sim_comm_init")
+            if self._gather is not None:
+                # direct NVLink halo: swap CUDA-IPC handles with the two ring neighbours
+                blob = (ctypes.c_char * 256)()
+                rt.check(rt.lib().lbm_sim_ipc_export(handle, blob), "lbm_sim_ipc_export")
+                blobs = self._gather(bytes(blob.raw))      # list of the blobs of all ranks, by rank
+                left = blobs[(self.rank - 1) % self.nranks]
+                right = blobs[(self.rank + 1) % self.nranks]
+                rt.check(rt.lib().lbm_sim_ipc_open(handle, left, right), "lbm_sim_ipc_open")
         self._time_dependent = False
 
     def __del__(self):

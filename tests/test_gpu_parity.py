@@ -129,3 +129,60 @@ def test_boundary_condition_only():
     sim.one_time_step()
     ora.one_time_step()
     assert np.abs(sim.container.F.get()[inner] - ora._F.swaparray[inner]).max() <= 1e-13
+
+
+# ---------------------------------------------------------------------------
+# directly against the REFERENCE fixtures (tests/golden, tools/make_golden.py)
+# ---------------------------------------------------------------------------
+import json
+import os
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("name,kw", PARITY_CASES, ids=[c[0] + "-" + "x".join(str(v) for v in c[1].values()) for c in PARITY_CASES])
+def test_cuda_against_reference_fixture(name, kw):
+    """boundary lists bit-exact, conserved moments after 50 steps within 1e-12 of the reference's
+    Cython generator (fixture produced by the unmodified pylbm)."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+    from conftest import case_id
+
+    ref = np.load(os.path.join(GOLDEN, "ref_%s.npz" % case_id(name, kw)))
+    sim = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw))
+    assert len(sim.bc.methods) == int(ref["nmethods"])
+    for i, method in enumerate(sim.bc.methods):
+        pre = "bc%d_" % i
+        assert type(method).__name__ == str(ref[pre + "name"])
+        assert method.istore.dtype == np.int32 and np.array_equal(method.istore, ref[pre + "istore"])
+        for j, il in enumerate(method.iload):
+            assert np.array_equal(il, ref[pre + "iload%d" % j])
+        if hasattr(method, "s"):
+            assert np.array_equal(method.s, ref[pre + "s"])
+        np.testing.assert_allclose(method.rhs, ref[pre + "rhs"], rtol=0, atol=1e-15)
+    sim.run(int(ref["nsteps"]))
+    fluid = ref["in_or_out"][tuple(slice(v, -v) for v in sim.domain.stencil.vmax)] == sim.domain.valin
+    for key in sim.scheme.consm:
+        a, b = sim.m[key], ref["m_" + str(key)]
+        err = np.abs(a[fluid] - b[fluid]).max() / np.abs(b[fluid]).max()
+        assert err <= TOL_F64, (str(key), err)
+
+
+def test_cuda_against_reference_golden_h5_fields():
+    """the reference's own golden fields (dx = 1/64, Tf = 0.5, solid cells zeroed)."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    manifest = json.load(open(os.path.join(GOLDEN, "MANIFEST.json")))
+    for fname, meta in manifest["files"].items():
+        if not fname.startswith("h5_"):
+            continue
+        ref = np.load(os.path.join(GOLDEN, fname))
+        sim = pylbm_b200.Simulation(cases.CASES[meta["case"]](**meta["kwargs"]))
+        while sim.t < meta["final_time"]:
+            sim.one_time_step()
+        solid = sim.domain.in_or_out[tuple(slice(v, -v) for v in sim.domain.stencil.vmax)] != sim.domain.valin
+        for key in sim.scheme.consm:
+            field = sim.m[key].copy()
+            field[solid] = 0
+            assert np.abs(field - ref[str(key)]).max() <= 1e-12, (fname, str(key))
