@@ -57,6 +57,19 @@ class KernelIR:
         self.scalars = scalars
 
 
+def _horner(expr, syms):
+    """polynomial in the relative-velocity symbols -> nested (Horner) form: fewer multiplications
+    than the fully expanded products (D3Q27 central moments: 2323 -> 1246 operations)."""
+    expr = sp.expand(expr)
+    used = [s for s in syms if expr.has(s)]
+    if not used:
+        return expr
+    try:
+        return sp.horner(expr, *used)
+    except Exception:
+        return expr
+
+
 def _recursive_sub(expr, replace):
     for _ in range(len(replace) + 1):
         new = expr.subs(replace)
@@ -158,7 +171,7 @@ class PullAlgorithm:
         stm += [(m[i], mraw[i]) for i in range(nc)]
         stm += [(self.rel_sym[d], self.rel_vel[d]) for d in range(self.dim)]
         shifted = self.Tu * sp.Matrix(mraw)
-        stm += [(m[i], sp.expand(shifted[i])) for i in range(nc, self.ns)]
+        stm += [(m[i], _horner(shifted[i], self.rel_sym)) for i in range(nc, self.ns)]
         return stm, mraw
 
     def _source_local(self):
@@ -167,7 +180,15 @@ class PullAlgorithm:
     def _relaxation_local(self):
         eq = self.eq
         if self.with_rel_vel:
-            eq = (self.Tu * eq).applyfunc(sp.expand)
+            eq = self.Tu * eq
+            if not self.source_eq:
+                # rel_u still equals its definition in terms of the (unchanged) conserved moments:
+                # substituting it collapses the shifted equilibria (central-moment equilibria are
+                # constants times the density), which the reference evaluates as long polynomials
+                rel = dict(zip(self.rel_sym, self.rel_vel))
+                eq = eq.applyfunc(lambda e: sp.factor(sp.cancel(sp.together(sp.expand(e.subs(rel))))))
+            else:
+                eq = eq.applyfunc(lambda e: _horner(e, self.rel_sym))
         stm = []
         for i in range(self.ns):
             if self.s[i] == 0:
@@ -180,7 +201,7 @@ class PullAlgorithm:
         if self.with_rel_vel:
             back = [sp.Symbol("mback%d" % i, real=True) for i in range(self.ns)]
             shifted = self.Tmu * sp.Matrix(m)
-            stm = [(back[i], sp.expand(shifted[i])) for i in range(self.ns)]
+            stm = [(back[i], _horner(shifted[i], self.rel_sym)) for i in range(self.ns)]
             return stm, self._linear(self.invM, back)
         return [], self._linear(self.invM, m)
 
@@ -193,7 +214,13 @@ class PullAlgorithm:
         stm += self._relaxation_local()
         if self.with_rel_vel:
             shifted = self.Tu * sp.Matrix(mraw)
-            stm += [(self.m[i], sp.expand(shifted[i])) for i in range(self.nconsm)]
+            if not self.source_eq:
+                # same remark: e.g. the shifted momentum q - u*rho is identically zero
+                rel = dict(zip(self.rel_sym, [e.subs(dict(zip(self.m, mraw))) for e in self.rel_vel]))
+                rows = [sp.factor(sp.cancel(sp.together(sp.expand(shifted[i].subs(rel))))) for i in range(self.nconsm)]
+            else:
+                rows = [_horner(shifted[i], self.rel_sym) for i in range(self.nconsm)]
+            stm += [(self.m[i], rows[i]) for i in range(self.nconsm)]
         stm += self._source_local()
         tail, outputs = self._m2f_local()
         stm += tail

@@ -96,6 +96,22 @@ def lower_statements(statements, outputs, cse=True):
     if not cse:
         return ssa, outs
 
+    # one reciprocal per distinct base: b**-n -> (1/b)**n, so that e.g. qx/rho, qy/rho and
+    # qx**2/rho**2 share a single fp64 division
+    recips = {}
+
+    def _recip(expr):
+        def repl(p):
+            base, n = p.base, -int(p.exp)
+            if base not in recips:
+                recips[base] = sp.Symbol("inv_%d" % len(recips), real=True)
+            return recips[base] ** n
+        return expr.replace(lambda e: e.is_Pow and e.exp.is_Integer and e.exp < 0, repl)
+
+    ssa = [(lhs, _recip(rhs)) for lhs, rhs in ssa]
+    outs = [_recip(o) for o in outs]
+    ssa = ssa + [(sym, 1 / base) for base, sym in recips.items()]
+
     # forward-substitute trivial copies / keep the statement structure for CSE
     exprs = [rhs for _, rhs in ssa] + outs
     names = sp.numbered_symbols("t_", real=True)
