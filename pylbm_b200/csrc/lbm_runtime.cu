@@ -496,9 +496,7 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
         const int w = desc->vmax[a];
         if ((desc->periodic_mask & (1 << a)) && w > 0 && desc->grid.n[a] - 2 * w >= 2 * w) s->wrap_mask |= (1 << a);
     }
-    // the fastest axis is refreshed by a lean copy kernel instead: its two boundary lanes per row would
-    // stretch the lifetime of half of the blocks of the fused kernel (measured: +0.3 ms at 512^3)
-    s->wrap_mask &= ~(1 << 2);
+    if (getenv("PYLBM_B200_NO_ZWRAP")) s->wrap_mask &= ~(1 << 2);   // debugging aid: lean copy kernel for z
     if (getenv("PYLBM_B200_NO_WRAP")) s->wrap_mask = 0;
     for (int a = 0; a < 3; ++a) {
         s->sel[a].n = 0;

@@ -230,6 +230,7 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
     const long long planestride = (long long)g.n[1] * g.pitch;
     const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
 %(loads)s
+%(prologue)s
 %(body)s
 %(stores)s
 %(images)s
@@ -260,13 +261,11 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
 # positions) -- for the populations whose velocity points from that ghost cell into the interior along
 # every axis of A.  Only those (population, image) pairs are stored; the other ghost entries are
 # scratch (they are also never refreshed in the reference's Fnew, simulation.py:417).
-_IMAGES_HEAD = r"""    if (g.wrap | (pr.lo != nullptr)) {
-        // offset of the image along each axis (0: none).  SLAB is the axis cut into slabs when several
-        // GPUs share the lattice: images across it are stored straight into the neighbour rank's
-        // ghost planes through its peer-mapped array (NVLink), see lbmk_peers.
-        long long d0 = 0, d1 = 0, d2 = 0;
-        %(tout)s* qbase = fout;          // array receiving the images that cross the SLAB axis
-        long long qps = g.pstride;
+_IMAGES_PROLOGUE = r"""    // ---- periodic / neighbour images of this cell (see the comment above _IMAGES_PROLOGUE) ----
+    long long d0 = 0, d1 = 0, d2 = 0;    // offset of the image along each axis (0: none)
+    %(tout)s* qbase = fout;              // array receiving the images that cross the SLAB axis
+    long long qps = g.pstride;
+    if (g.wrap | (pr.lo != nullptr)) {
         const long long stride_[3] = {planestride, rowstride, 1};
         const int idx_[3] = {i0, i1, i2};
         long long d_[3] = {0, 0, 0};
@@ -284,37 +283,50 @@ _IMAGES_HEAD = r"""    if (g.wrap | (pr.lo != nullptr)) {
             }
         }
         d0 = d_[0]; d1 = d_[1]; d2 = d_[2];
-        if (d0 | d1 | d2) {   // rare: only the cells within w of a face
-            // an image in a HIGH ghost layer (d > 0) is read by populations moving in -axis, and vice versa
-            const bool p0 = d0 < 0, m0 = d0 > 0, p1 = d1 < 0, m1 = d1 > 0, p2 = d2 < 0, m2 = d2 > 0;
-            (void)p0; (void)m0; (void)p1; (void)m1; (void)p2; (void)m2;
+    }
+    // an image in a HIGH ghost layer (d > 0) is read by populations moving in -axis, and vice versa
+    const bool p0 = d0 < 0, m0 = d0 > 0, p1 = d1 < 0, m1 = d1 > 0, p2 = d2 < 0, m2 = d2 > 0;
+    (void)p0; (void)m0; (void)p1; (void)m1; (void)p2; (void)m2; (void)qbase; (void)qps;
 """
 
 
+def _inline_image(v, k, slab):
+    """store suffix for the image that only crosses the FASTEST axis (two lanes of every row): done
+    with the main store from the register value -- no re-read, no divergent tail."""
+    if v[2] == 0:
+        return ""
+    cond = "p2" if v[2] > 0 else "m2"
+    if slab == 2:
+        return " if (%s) qbase[%dLL * qps + cell + d2] = o_;" % (cond, k)
+    return " if (%s) p_[d2] = o_;" % cond
+
+
 def _images_code(velocities, tout, slab):
-    """tail of the fused kernel: stores of the needed (population, image) pairs."""
+    """tail of the fused kernel: stores of the needed (population, image) pairs that cross axis 0
+    or 1 (cells of whole boundary rows / planes: full warps, rare)."""
     import itertools
 
-    lines = [_IMAGES_HEAD % dict(tout=tout)]
+    lines = ["    if (d0 | d1) {"]
     dname = ["d0", "d1", "d2"]
-    moving = [k for k, v in enumerate(velocities) if any(c != 0 for c in v)]
+    moving = [k for k, v in enumerate(velocities) if v[0] != 0 or v[1] != 0]
     # re-read this thread's own stores, all loads issued back to back (one memory latency)
     for k in moving:
-        lines.append("            const %s v%d_ = fout[%dLL * g.pstride + cell];" % (tout, k, k))
+        lines.append("        const %s v%d_ = fout[%dLL * g.pstride + cell];" % (tout, k, k))
     for k in moving:
         v = velocities[k]
         axes = [a for a in range(3) if v[a] != 0]
         conds = {a: ("p%d" % a if v[a] > 0 else "m%d" % a) for a in axes}
         for r in range(1, len(axes) + 1):
             for sub in itertools.combinations(axes, r):
+                if sub == (2,):
+                    continue   # done inline with the main store
                 cond = " && ".join(conds[a] for a in sub)
                 off = " + ".join(dname[a] for a in sub)
                 if slab in sub:
                     target = "qbase[%dLL * qps + cell + %s]" % (k, off)
                 else:
                     target = "fout[%dLL * g.pstride + cell + %s]" % (k, off)
-                lines.append("            if (%s) %s = v%d_;" % (cond, target, k))
-    lines.append("        }")
+                lines.append("        if (%s) %s = v%d_;" % (cond, target, k))
     lines.append("    }")
     return "\n".join(lines)
 
@@ -360,10 +372,18 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
             % (sym, k, _offset_expr(_canonical(off)))
         )
     body = ["    const double %s = %s;" % (lhs, _printer.doprint(rhs)) for lhs, rhs in temps]
-    stores = [
-        "    fout[%d * g.pstride + cell] = (%s)(%s);" % (k, tout, _printer.doprint(o))
-        for k, o in enumerate(outs)
-    ]
+    if images:
+        vels = [tuple(-o for o in _canonical(off)) for off in ir.in_offsets]
+        stores = [
+            "    { const %s o_ = (%s)(%s); %s* p_ = fout + (%dLL * g.pstride + cell); *p_ = o_;%s }"
+            % (tout, tout, _printer.doprint(o), tout, k, _inline_image(vels[k], k, slab))
+            for k, o in enumerate(outs)
+        ]
+    else:
+        stores = [
+            "    fout[%d * g.pstride + cell] = (%s)(%s);" % (k, tout, _printer.doprint(o))
+            for k, o in enumerate(outs)
+        ]
     add, mul, div = count_ops(temps, outs)
     scal_params = "".join(", const double %s" % _c_name(s) for s in ir.scalars)
     scal_args = "".join(", scalars[%d]" % i for i in range(len(ir.scalars)))
@@ -379,6 +399,7 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         scalar_args=scal_args,
         loads="\n".join(loads),
         images=_images_code([tuple(-o for o in _canonical(off)) for off in ir.in_offsets], tout, slab) if images else "",
+        prologue=(_IMAGES_PROLOGUE % dict(tout=tout)) if images else "",
         peer_param=", const lbmk_peers pr" if images else "",
         peer_arg=", (peers ? *peers : lbmk_peers{nullptr, nullptr, 0, 0, 0})" if images else "",
         launch_head=(_LAUNCH_HEAD_PEERS if images else _LAUNCH_HEAD) % dict(name=ir.name),
