@@ -338,3 +338,230 @@ CASES = {
     "lid_cavity_d3q19": lid_cavity_d3q19,
     "channel_sphere_d3q27": channel_sphere_d3q27,
 }
+
+
+# --------------------------------------------------------------------------
+# additional parity workloads (features of the reference demos not covered by C1-C5)
+# --------------------------------------------------------------------------
+T = sp.symbols("T")
+U = sp.symbols("u")
+
+
+def _rb_init_T(x, y, Td, Tu, xmin, xmax, ymin, ymax):
+    xmid, ymid = (xmax + xmin) / 2, (ymax + ymin) / 2
+    return Td + (Tu - Td) / (ymax - ymin) * (y - ymin) + Td * (x < 1.1 * xmid) * (x > 0.9 * xmid) * (y < ymid)
+
+
+def _rb_up(f, m, x, y, Tu):
+    m[QX] = 0.0
+    m[QY] = 0.0
+    m[T] = Tu
+
+
+def _rb_down(f, m, x, y, Td):
+    m[QX] = 0.0
+    m[QY] = 0.0
+    m[T] = Td
+
+
+def _rb_down_with_time(f, m, t, x, y, Td, Tu):
+    m[QX] = 0.0
+    m[QY] = 0.0
+    if 0 <= t % 10.0 <= 5:
+        m[T] = Td
+    else:
+        m[T] = Tu
+
+
+def rayleigh_benard(nx=128, ny=64, mod=None, perturb=None, generator="cuda", time_bc=True, period=10.0):
+    """D2Q9 (fluid, source term alpha*g*T on qy) coupled to D2Q5 (temperature): Bouzidi bounce-back
+    on the fluid and Bouzidi ANTI bounce-back on the temperature, periodic in x, bottom value that
+    depends on time (demo/2D/Rayleigh-Benard.py:62-232; reference golden test2D_rayleigh_benard.h5
+    is nx=128, ny=64, Tf=0.5, time_bc=True)."""
+    mod = mod or _default_mod()
+    Td, Tu = 0.5, -0.5
+    xmin, xmax, ymin, ymax = 0.0, 2.0, 0.0, 1.0
+    dx = (ymax - ymin) / ny
+    Ra, Pr, alpha, la, g = 2000, 0.71, 0.005, 1.0, 9.81
+    nu = np.sqrt(Pr * alpha * 9.81 * (Td - Tu) * (ymax - ymin) / Ra)
+    kappa = nu / Pr
+    eta = nu
+    snu = 1.0 / (0.5 + 3 * nu)
+    seta = 1.0 / (0.5 + 3 * eta)
+    sq = 8 * (2 - snu) / (8 - snu)
+    sf = [0.0, 0.0, 0.0, seta, seta, sq, sq, snu, snu]
+    a = 0.5
+    skappa = 1.0 / (0.5 + 10 * kappa / (4 + a))
+    se = 1.0 / (0.5 + np.sqrt(3) / 3)
+    sT = [0.0, skappa, skappa, se, se]
+
+    if period != 10.0:
+        def down_t(f, m, t, x, y, Td, Tu):
+            m[QX] = 0.0
+            m[QY] = 0.0
+            m[T] = Td if 0 <= t % period <= period / 2 else Tu
+    else:
+        down_t = _rb_down_with_time
+    methods = {0: mod.bc.BouzidiBounceBack, 1: mod.bc.BouzidiAntiBounceBack}
+    if time_bc:
+        bottom = {"method": dict(methods), "value": (down_t, (Td, Tu)), "time_bc": True}
+    else:
+        bottom = {"method": dict(methods), "value": (_rb_down, (Td,))}
+    init = {RHO: 1.0, QX: 0.0, QY: 0.0, T: (_rb_init_T, (Td, Tu, xmin, xmax, ymin, ymax))}
+    if perturb is not None:
+        init[QX] = _perturbed(perturb + 1, 0.0)
+        init[QY] = _perturbed(perturb + 2, 0.0)
+    return {
+        "box": {"x": [xmin, xmin + nx * dx], "y": [ymin, ymax], "label": [-1, -1, 0, 1]},
+        "space_step": dx,
+        "scheme_velocity": la,
+        "schemes": [
+            {
+                "velocities": list(range(9)),
+                "conserved_moments": [RHO, QX, QY],
+                "polynomials": [
+                    1, X, Y, 3 * (X**2 + Y**2) - 4,
+                    0.5 * (9 * (X**2 + Y**2) ** 2 - 21 * (X**2 + Y**2) + 8),
+                    3 * X * (X**2 + Y**2) - 5 * X, 3 * Y * (X**2 + Y**2) - 5 * Y, X**2 - Y**2, X * Y,
+                ],
+                "relaxation_parameters": sf,
+                "equilibrium": [
+                    RHO, QX, QY, -2 * RHO + 3 * (QX**2 + QY**2), RHO - 3 * (QX**2 + QY**2),
+                    -QX, -QY, QX**2 - QY**2, QX * QY,
+                ],
+                "source_terms": {QY: alpha * g * T},
+            },
+            {
+                "velocities": list(range(5)),
+                "conserved_moments": T,
+                "polynomials": [1, X, Y, 5 * (X**2 + Y**2) - 4, (X**2 - Y**2)],
+                "equilibrium": [T, T * QX, T * QY, a * T, 0.0],
+                "relaxation_parameters": sT,
+            },
+        ],
+        "init": init,
+        "boundary_conditions": {0: bottom, 1: {"method": dict(methods), "value": (_rb_up, (Tu,))}},
+        "generator": generator,
+    }
+
+
+def _bump(x, xmin, xmax):
+    mid, width = 0.5 * (xmin + xmax), 0.125 * (xmax - xmin)
+    return np.exp(-((x - mid) / width) ** 2)
+
+
+def _u_left(f, m, x, value):
+    m[U] = value
+
+
+def advection_d1q5(n=128, mod=None, perturb=None, generator="cuda"):
+    """1-D advection, D1Q5 (velocities up to +-2: two ghost layers per side), Neumann outflow on the
+    right and a prescribed value with bounce-back on the left."""
+    mod = mod or _default_mod()
+    xmin, xmax = 0.0, 1.0
+    dx = (xmax - xmin) / n
+    c = 0.4
+    init = {U: (_bump, (xmin, xmax))}
+    if perturb is not None:
+        init = {U: _perturbed(perturb, 0.5, amp=0.2)}
+    return {
+        "box": {"x": [xmin, xmax], "label": [0, 1]},
+        "space_step": dx,
+        "scheme_velocity": 1.0,
+        "schemes": [
+            {
+                "velocities": list(range(5)),
+                "conserved_moments": U,
+                "polynomials": [1, X, X**2 / 2, X**3 / 6, X**4 / 24],
+                "equilibrium": [U, c * U, c**2 * U / 2 + U / 6, c**3 * U / 6, c**4 * U / 24],
+                "relaxation_parameters": [0.0, 1.5, 1.2, 1.0, 1.3],
+            }
+        ],
+        "init": init,
+        "boundary_conditions": {
+            0: {"method": {0: mod.bc.BounceBack}, "value": (_u_left, (0.25,))},
+            1: {"method": {0: mod.bc.Neumann}},
+        },
+        "generator": generator,
+    }
+
+
+def _t_wall(f, m, x, y, value):
+    m[T] = value
+
+
+def heat_d2q5(n=48, mod=None, perturb=None, generator="cuda"):
+    """2-D heat equation, D2Q5 with anti bounce-back (Dirichlet) walls, a solid triangle and an
+    elliptic hole treated with Bouzidi anti bounce-back, Neumann in y on the top wall."""
+    mod = mod or _default_mod()
+    dx = 1.0 / n
+    init = {T: 0.0}
+    if perturb is not None:
+        init = {T: _perturbed(perturb, 0.5, amp=0.3)}
+    return {
+        "box": {"x": [0.0, 1.0], "y": [0.0, 1.0], "label": [0, 1, 2, 3]},
+        "elements": [
+            mod.Triangle([0.15, 0.2], [0.3, 0.05], [0.05, 0.3], label=4),
+            mod.Ellipse([0.65, 0.6], [0.2, 0.1], [-0.05, 0.1], label=5),
+        ],
+        "space_step": dx,
+        "scheme_velocity": 1.0,
+        "schemes": [
+            {
+                "velocities": list(range(5)),
+                "conserved_moments": T,
+                "polynomials": [1, X, Y, (X**2 + Y**2) / 2, (X**2 - Y**2) / 2],
+                "equilibrium": [T, 0.0, 0.0, 0.4 * T, 0.0],
+                "relaxation_parameters": [0.0, 1.2, 1.2, 1.5, 1.1],
+            }
+        ],
+        "init": init,
+        "boundary_conditions": {
+            0: {"method": {0: mod.bc.AntiBounceBack}, "value": (_t_wall, (1.0,))},
+            1: {"method": {0: mod.bc.AntiBounceBack}, "value": (_t_wall, (0.0,))},
+            2: {"method": {0: mod.bc.AntiBounceBack}, "value": (_t_wall, (0.5,))},
+            3: {"method": {0: mod.bc.NeumannY}},
+            4: {"method": {0: mod.bc.BouzidiAntiBounceBack}, "value": (_t_wall, (0.25,))},
+            5: {"method": {0: mod.bc.BouzidiAntiBounceBack}, "value": (_t_wall, (0.75,))},
+        },
+        "generator": generator,
+    }
+
+
+def advection_d3q6(n=16, mod=None, perturb=None, generator="cuda"):
+    """3-D advection, D3Q6, fully periodic, initialisation on the DISTRIBUTIONS (inittype)."""
+    dx = 1.0 / n
+    cx, cy, cz = 0.2, 0.1, -0.1
+
+    def blob(x, y, z):
+        return 1.0 + np.exp(-40 * ((x - 0.5) ** 2 + (y - 0.5) ** 2 + (z - 0.5) ** 2))
+
+    if perturb is not None:
+        finit = {k: _perturbed(perturb + k, 1.0 / 6, amp=0.05) for k in range(6)}
+    else:
+        finit = {k: (lambda x, y, z: blob(x, y, z) / 6) for k in range(6)}
+    return {
+        "box": {"x": [0.0, 1.0], "y": [0.0, 1.0], "z": [0.0, 1.0], "label": -1},
+        "space_step": dx,
+        "scheme_velocity": 1.0,
+        "schemes": [
+            {
+                "velocities": list(range(1, 7)),
+                "conserved_moments": U,
+                "polynomials": [1, X, Y, Z, X**2 - Y**2, X**2 - Z**2],
+                "equilibrium": [U, cx * U, cy * U, cz * U, 0.0, 0.0],
+                "relaxation_parameters": [0.0, 1.6, 1.6, 1.6, 1.3, 1.3],
+            }
+        ],
+        "inittype": "distributions",
+        "init": finit,
+        "generator": generator,
+    }
+
+
+CASES.update({
+    "rayleigh_benard": rayleigh_benard,
+    "advection_d1q5": advection_d1q5,
+    "heat_d2q5": heat_d2q5,
+    "advection_d3q6": advection_d3q6,
+})

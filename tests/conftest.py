@@ -30,4 +30,9 @@ PARITY_CASES = [
     ("shallow_water_d2q4", dict(n=32)),
     ("lid_cavity_d3q19", dict(n=16)),
     ("channel_sphere_d3q27", dict(nx=32, ny=16, nz=16)),
+    # features of the reference demos not covered by the BASELINE configs
+    ("rayleigh_benard", dict(nx=64, ny=32, period=0.2)),   # 2 schemes, source term, Bouzidi anti-BB, time_bc
+    ("advection_d1q5", dict(n=64)),                        # 1-D, ghost width 2, Neumann, bounce-back value
+    ("heat_d2q5", dict(n=32)),                             # anti-BB, Bouzidi anti-BB, NeumannY, triangle, ellipse
+    ("advection_d3q6", dict(n=12)),                        # 3-D periodic, init on distributions
 ]

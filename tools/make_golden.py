@@ -153,7 +153,7 @@ def reference_fixture(case, kw, nsteps=NSTEPS):
         out[pre + "istore"] = method.istore
         for j, il in enumerate(method.iload):
             out[pre + "iload%d" % j] = il
-        out[pre + "rhs"] = method.rhs
+        out[pre + "rhs"] = method.rhs.copy()
         out[pre + "ilabel"] = method.ilabel
         out[pre + "distance"] = method.distance
         if hasattr(method, "s"):
@@ -179,15 +179,19 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     manifest = {"reference": "pylbm 0.11.0 (unmodified, /root/reference) with the Cython generator",
                 "nsteps": NSTEPS, "files": {}}
+    only = sys.argv[1] if len(sys.argv) > 1 else None
     for case, kw in PARITY_CASES:
         name = "ref_%s.npz" % case_id(case, kw)
+        manifest["files"][name] = {"case": case, "kwargs": kw, "perturb": 0}
+        if only is not None and only not in name and os.path.exists(os.path.join(OUT, name)):
+            continue
         print("reference run:", name, flush=True)
         np.savez_compressed(os.path.join(OUT, name), **reference_fixture(case, kw))
-        manifest["files"][name] = {"case": case, "kwargs": kw, "perturb": 0}
     for h5, case, kw, steps in [
         ("test2D_lid_driven_cavity.h5", "lid_cavity_d2q9", dict(n=64), 32),
         ("test2D_karman_vortex_street.h5", "karman_d2q9", dict(nx=128, ny=64, radius=1.0 / 32, cx=0.3), 32),
         ("test2D_shallow_water.h5", "shallow_water_d2q4", dict(n=128), None),
+        ("test2D_rayleigh_benard.h5", "rayleigh_benard", dict(nx=128, ny=64), None),
     ]:
         fields = convert_h5(h5)
         name = "h5_" + h5.replace(".h5", ".npz")
