@@ -118,7 +118,7 @@ def test_module_object_built_from_a_reference_simulation(pylbm):
     for r in routines:
         fn = getattr(module, r.name)
         assert callable(fn) and isinstance(fn.arg_dict, dict)
-        wanted = {a.name for a in r.arguments}
+        wanted = {str(a.name) for a in r.arguments}
         if r.name in BC_ROUTINES:
             assert set(fn.arg_dict) <= wanted
         else:
