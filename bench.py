@@ -45,7 +45,11 @@ WORKLOADS = {
     "d2q9_lid_256": ("lid_cavity_d2q9", dict(n=256), "D2Q9 lid-driven cavity 256^2 (BASELINE config 1)"),
     "d3q27_channel_512x256x256": ("channel_sphere_d3q27", dict(nx=512, ny=256, nz=256),
                                   "D3Q27 channel with sphere 512x256x256 (BASELINE config 5, one slab)"),
+    # weak scaling: nx is multiplied by the number of GPUs (128 x 1024 x 1024 cells per GPU -> 1024^3 on 8)
+    "d3q27_channel_weak": ("channel_sphere_d3q27", dict(nx=128, ny=1024, nz=1024),
+                           "D3Q27 channel with sphere, weak scaling 128x1024x1024 per GPU (BASELINE config 5)"),
 }
+WEAK = {"d3q27_channel_weak"}
 DEFAULT_WORKLOAD = "d3q19_lid_512"
 
 
@@ -213,6 +217,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     case_name, case_kw, description = WORKLOADS[args.workload]
+    scaling = "weak" if args.workload in WEAK else "strong"
+    if scaling == "weak":
+        case_kw = dict(case_kw, nx=case_kw["nx"] * world)
     q_of = {"lid_cavity_d3q19": 19, "karman_d2q9": 9, "shallow_water_d2q4": 12, "lid_cavity_d2q9": 9,
             "channel_sphere_d3q27": 27}
     config = {"workload": description, "case": case_name, **case_kw, "storage": args.dtype,
@@ -226,7 +233,7 @@ def main():
         line = {
             "impl": "reference", "metric": "MLUPS", "value": res["value"], "unit": "MLUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": config,
             "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": res["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -382,7 +389,7 @@ def main():
         line = {
             "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32-storage/f64-math",
+            "scaling": scaling, "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32-storage/f64-math",
             "data": "synthetic", "config": dict(config, parallelism="x-slabs x%d" % world, setup_s=round(t_build, 2),
                            halo=(args.halo if world > 1 else "periodic (single GPU)")),
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),

@@ -139,8 +139,6 @@ int lbm_sim_set_state(lbm_sim* sim, void* f, void* fnew, double t);
 int lbm_sim_invalidate_ghosts(lbm_sim* sim);
 /* capture pairs of steps in a CUDA graph (only when the kernel does not depend on t) */
 int lbm_sim_use_graph(lbm_sim* sim, int enable);
-/* overlap the slab exchange with the interior update (multi-GPU) */
-int lbm_sim_set_overlap(lbm_sim* sim, int enable);
 /* CUDA-event timer on the stream the kernels are launched on */
 int lbm_sim_timer_start(lbm_sim* sim);
 int lbm_sim_timer_stop(lbm_sim* sim, float* elapsed_ms);

@@ -21,7 +21,6 @@ scatter.  Bouzidi bounce-back reads a snapshot taken when the method starts
 """
 
 import collections
-import types
 
 import numpy as np
 

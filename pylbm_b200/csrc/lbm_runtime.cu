@@ -445,7 +445,6 @@ struct lbm_sim {
     nccl_comm comm = nullptr;
     int rank = 0, nranks = 1;
     int slab_axis = 0;
-    int overlap = 0;
     // direct NVLink halo (CUDA IPC): peer arrays [side lo/hi][buffer A/B], arrival counters
     int peers_ready = 0;
     long long signals = 0, waits = 0;             // enqueued so far (host-side bookkeeping)
@@ -836,12 +835,6 @@ extern "C" int lbm_sim_use_graph(lbm_sim* s, int enable) {
     if (!s) return ARG_ERROR("null sim");
     s->use_graph = enable ? 1 : 0;
     if (!enable) drop_graph(s);
-    return 0;
-}
-
-extern "C" int lbm_sim_set_overlap(lbm_sim* s, int enable) {
-    if (!s) return ARG_ERROR("null sim");
-    s->overlap = enable ? 1 : 0;
     return 0;
 }
 

@@ -9,7 +9,7 @@ fallback path in the product.
 import ctypes
 import json
 from ctypes import (
-    POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_uint8, c_uint64, c_void_p,
+    POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p,
 )
 
 from . import build
@@ -105,7 +105,6 @@ _SIGNATURES = {
     "lbm_sim_set_state": (c_int, [c_void_p, c_void_p, c_void_p, c_double]),
     "lbm_sim_invalidate_ghosts": (c_int, [c_void_p]),
     "lbm_sim_use_graph": (c_int, [c_void_p, c_int]),
-    "lbm_sim_set_overlap": (c_int, [c_void_p, c_int]),
     "lbm_sim_timer_start": (c_int, [c_void_p]),
     "lbm_sim_timer_stop": (c_int, [c_void_p, POINTER(c_float)]),
     "lbm_sim_profile": (c_int, [c_void_p, c_int]),

@@ -32,7 +32,7 @@ from .boundary import Boundary
 from .cudagen import generate_source
 from .domain import Domain, SlabTopology
 from .scheme import Scheme
-from .storage import DeviceArray, HostArray
+from .storage import DeviceArray
 
 __all__ = ["Simulation", "CudaContainer"]
 
