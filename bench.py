@@ -335,7 +335,7 @@ def main():
     peak, peak_src = measured_peak()
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.dtype == "float64":
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
