@@ -81,6 +81,10 @@ def build_runtime(force=False, verbose=False):
     return lib
 
 
+def kernel_library_path(tag):
+    return os.path.join(BUILD_DIR, "liblbmk_%s.so" % tag)
+
+
 def build_kernels(source, tag, force=False, keep_source=True, extra_flags=()):
     """compile a generated translation unit -> _build/liblbmk_<tag>.so (cached by tag)."""
     os.makedirs(BUILD_DIR, exist_ok=True)

@@ -451,6 +451,26 @@ def default_minblocks(nv):
     return 5
 
 
+def kernel_tag(kernels, dim, nv, storage="double", cse=True):
+    """
+    Cache key of a kernel library: hash of the IR (deterministic across processes, unlike the text
+    produced by sympy.cse whose temporaries depend on set ordering), of the generator options and
+    of this generator's own source.
+    """
+    h = hashlib.sha256()
+    with open(__file__.replace(".pyc", ".py"), "rb") as fh:
+        h.update(fh.read())
+    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv))).encode())
+    for ir in kernels:
+        h.update(repr((ir.name, ir.in_array, ir.out_array, bool(ir.inner), list(ir.scalars),
+                       [str(s) for s in ir.in_syms], [tuple(o) for o in ir.in_offsets])).encode())
+        for lhs, rhs in ir.statements:
+            h.update((str(lhs) + "=" + sp.srepr(sp.sympify(rhs))).encode())
+        for out in ir.outputs:
+            h.update(sp.srepr(sp.sympify(out)).encode())
+    return h.hexdigest()[:20]
+
+
 def generate_source(kernels, dim, nv, storage="double", cse=True):
     """
     Full translation unit for a list of KernelIR.  Returns (source, info dict).
@@ -475,5 +495,5 @@ def generate_source(kernels, dim, nv, storage="double", cse=True):
     literal = '"' + text.replace("\\", "\\\\").replace('"', '\\"') + '"'
     parts.append(_DESCRIBE % dict(json=literal))
     source = "\n".join(parts)
-    info["hash"] = hashlib.sha256(source.encode()).hexdigest()[:20]
+    info["hash"] = kernel_tag(kernels, dim, nv, storage, cse)
     return source, info

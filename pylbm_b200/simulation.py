@@ -29,7 +29,7 @@ from . import runtime as rt
 from . import build
 from .algorithm import PullAlgorithm
 from .boundary import Boundary
-from .cudagen import generate_source
+from .cudagen import generate_source, kernel_tag
 from .domain import Domain, SlabTopology
 from .scheme import Scheme
 from .storage import DeviceArray
@@ -37,7 +37,7 @@ from .storage import DeviceArray
 __all__ = ["Simulation", "CudaContainer"]
 
 
-def build_kernel_library(scheme, settings=None, storage="f64"):
+def build_kernel_library(scheme, settings=None, storage="f64", need_source=False):
     """
     scheme -> per-cell kernel IR -> CUDA C -> liblbmk_<hash>.so (cached in-tree by source hash).
     Needs nvcc but no GPU, so it is also what `__graft_entry__.build()` runs on the build box.
@@ -47,7 +47,11 @@ def build_kernel_library(scheme, settings=None, storage="f64"):
     algo_settings.update(settings or {})
     algo = PullAlgorithm(scheme, algo_settings)
     c_storage = "double" if storage == "f64" else "float"
-    source, info = generate_source(algo.kernels(), scheme.dim, algo.ns, storage=c_storage)
+    kernels = algo.kernels()
+    path = build.kernel_library_path(kernel_tag(kernels, scheme.dim, algo.ns, storage=c_storage))
+    if os.path.exists(path) and not need_source:
+        return algo, path, None          # cached: no lowering, no nvcc
+    source, info = generate_source(kernels, scheme.dim, algo.ns, storage=c_storage)
     return algo, build.build_kernels(source, info["hash"]), source
 
 
@@ -148,10 +152,12 @@ class Simulation:
 
         # ---- generated kernels -----------------------------------------
         user_algo = dico.get("lbm_algorithm", None) or {}
-        self.algo, lib_path, source = build_kernel_library(self.scheme, user_algo.get("settings", {}), storage)
+        codegen_opt = dico.get("codegen_option", None)
+        want_source = bool(dico.get("show_code", False) or (codegen_opt and codegen_opt.get("directory")))
+        self.algo, lib_path, source = build_kernel_library(self.scheme, user_algo.get("settings", {}), storage,
+                                                           need_source=want_source)
         if dico.get("show_code", False):
             print(source)
-        codegen_opt = dico.get("codegen_option", None)
         if codegen_opt and codegen_opt.get("directory"):
             outdir = os.path.realpath(codegen_opt["directory"])
             os.makedirs(outdir, exist_ok=True)

@@ -35,7 +35,7 @@ def test_generated_library_exports_lbmk_symbols():
     from pylbm_b200.scheme import Scheme
     from pylbm_b200.simulation import build_kernel_library
 
-    _, path, source = build_kernel_library(Scheme(cases.karman_d2q9(nx=128, ny=32)))
+    _, path, source = build_kernel_library(Scheme(cases.karman_d2q9(nx=128, ny=32)), need_source=True)
     lib = ctypes.CDLL(path)
     declared = [n for n in _declared("lbmk.h") if n != "lbmk_source_term"]   # only with source terms
     for name in declared:
