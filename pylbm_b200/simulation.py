@@ -312,10 +312,19 @@ class Simulation:
         else:
             rt.check(rt.lib().lbm_device_sync(), "sync")
 
+    def _scratch(self, nv, ncell, storage, slot):
+        """cached 1-D device arrays for the small wall-value evaluations (time-dependent boundary
+        values call them every step)."""
+        cache = self.__dict__.setdefault("_scratch_arrays", {})
+        key = (nv, ncell, storage, slot)
+        if key not in cache:
+            cache[key] = DeviceArray(nv, (ncell,), [0], storage)
+        return cache[key]
+
     def _on_device(self, host):
-        """temporary 1-D device twin of a small HostArray (kernels are shape agnostic)."""
+        """1-D device twin of a small HostArray (kernels are shape agnostic)."""
         ncell = int(np.prod(host.nspace))
-        dev = DeviceArray(host.nv, (ncell,), [0], "f64")
+        dev = self._scratch(host.nv, ncell, "f64", 0)
         dev.set(host.array.reshape(host.nv, ncell))
         return dev
 
@@ -330,7 +339,7 @@ class Simulation:
     def m2f(self, m_user=None, f_user=None, **kwargs):
         if m_user is not None:
             dm = self._on_device(m_user)
-            df = DeviceArray(dm.nv, dm.nspace, [0], self.storage)
+            df = self._scratch(dm.nv, dm.nspace[0], self.storage, 1)
             self._launch("m2f", dm, df)
             f_user.array[...] = df.get().reshape(f_user.array.shape)
             return

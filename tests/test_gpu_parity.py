@@ -186,3 +186,57 @@ def test_cuda_against_reference_golden_h5_fields():
             field = sim.m[key].copy()
             field[solid] = 0
             assert np.abs(field - ref[str(key)]).max() <= 1e-12, (fname, str(key))
+
+
+def test_split_step_equals_fused_step():
+    """boundary_condition -> transport -> f2m -> relaxation -> m2f (the stand-alone kernels, reference
+    simulation.py:392-408 docstring) reproduces one_time_step for a scheme without relative velocity."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    kw = dict(n=12)
+    a = pylbm_b200.Simulation(cases.lid_cavity_d3q19(perturb=1, **kw))
+    b = pylbm_b200.Simulation(cases.lid_cavity_d3q19(perturb=1, **kw))
+    for _ in range(3):
+        a.one_time_step()
+        b.boundary_condition()
+        b.transport()
+        b.f2m()
+        b.relaxation()
+        b.m2f()
+    inner = (slice(None),) + (slice(1, -1),) * 3
+    Fa, Fb = a.container.F.get()[inner], b.container.F.get()[inner]
+    assert np.abs(Fa - Fb).max() <= 1e-13 * np.abs(Fa).max()
+
+
+def test_runtime_scalars_from_extra_parameters():
+    """a symbol left free in the dictionary is a runtime scalar of the kernels, given through
+    sol.extra_parameters (reference: algorithm/base.py:662-667)."""
+    import sympy as sp
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    grav = sp.Symbol("gravity_coeff")
+    d_num = cases.rayleigh_benard(nx=32, ny=16, time_bc=False)
+    d_sym = cases.rayleigh_benard(nx=32, ny=16, time_bc=False)
+    num = d_num["schemes"][0]["source_terms"][cases.QY]          # alpha * g * T  (numbers)
+    coeff = float(num.coeff(cases.T))
+    d_sym["schemes"][0]["source_terms"] = {cases.QY: grav * cases.T}
+    a = pylbm_b200.Simulation(d_num)
+    b = pylbm_b200.Simulation(d_sym)
+    assert "gravity_coeff" in b.kernels.scalars("one_time_step")
+    b.extra_parameters[grav] = coeff
+    for _ in range(10):
+        a.one_time_step()
+        b.one_time_step()
+    for key in a.scheme.consm:
+        assert np.abs(a.m[key] - b.m[key]).max() <= 1e-14
+    # m_halo / F_halo setters
+    rho = a.m_halo[cases.RHO]
+    assert rho.shape == tuple(a.domain.shape_halo)
+    f0 = a.F_halo[0]
+    a.F_halo[0] = f0 * 1.0
+    a.one_time_step()
+    b.one_time_step()
+    for key in a.scheme.consm:
+        assert np.abs(a.m[key] - b.m[key]).max() <= 1e-14
