@@ -211,21 +211,16 @@ _KERNEL = r"""
 __global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
 lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g%(peer_param)s%(scalar_params)s)
 {
+    // 3-D grid: x = chunk of the fastest axis, y = group of `ty` rows of axis 1, z = index of axis 0
+    // (no integer division in the prologue; tx is a power of two)
     const unsigned tid = threadIdx.x;
     const unsigned tx = (unsigned)g.tx;
-    const unsigned ty = LBMK_BLOCK / tx;
-    const unsigned nchunk = ((unsigned)(g.hi[2] - g.lo[2]) + tx - 1) / tx;
-    const unsigned bid = blockIdx.x;
-    const unsigned rowblock = bid / nchunk;
-    const unsigned chunk = bid - rowblock * nchunk;
-    const int i2 = g.lo[2] + (int)(chunk * tx + (tid & (tx - 1)));
-    const unsigned n1in = (unsigned)(g.hi[1] - g.lo[1]);
-    const unsigned row = rowblock * ty + tid / tx;
-    const unsigned nrows = (unsigned)(g.hi[0] - g.lo[0]) * n1in;
-    if (i2 >= g.hi[2] || row >= nrows) return;
-    const unsigned r0 = row / n1in;
-    const int i0 = g.lo[0] + (int)r0;
-    const int i1 = g.lo[1] + (int)(row - r0 * n1in);
+    const unsigned txshift = 31u - (unsigned)__clz(tx);
+    const unsigned ty = LBMK_BLOCK >> txshift;
+    const int i2 = g.lo[2] + (int)(blockIdx.x * tx + (tid & (tx - 1)));
+    const int i1 = g.lo[1] + (int)(blockIdx.y * ty + (tid >> txshift));
+    const int i0 = g.lo[0] + (int)blockIdx.z;
+    if (i2 >= g.hi[2] || i1 >= g.hi[1]) return;
     const long long rowstride = g.pitch;
     const long long planestride = (long long)g.n[1] * g.pitch;
     const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
@@ -238,14 +233,13 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
 
 %(launch_head)s
 {
-    const long long nrows = (long long)(g->hi[0] - g->lo[0]) * (g->hi[1] - g->lo[1]);
-    const int n2 = g->hi[2] - g->lo[2];
-    if (nrows <= 0 || n2 <= 0) return 0;
+    const int n0 = g->hi[0] - g->lo[0], n1 = g->hi[1] - g->lo[1], n2 = g->hi[2] - g->lo[2];
+    if (n0 <= 0 || n1 <= 0 || n2 <= 0) return 0;
+    if (g->tx <= 0 || (g->tx & (g->tx - 1)) || g->tx > LBMK_BLOCK) return -3;
     const int ty = LBMK_BLOCK / g->tx;
-    const long long nchunk = (n2 + g->tx - 1) / g->tx;
-    const long long nblocks = nchunk * ((nrows + ty - 1) / ty);
-    if (nblocks > 2147483647LL || nrows > 2147483647LL) return -2;
-    lbmk_kernel_%(name)s<<<(unsigned)nblocks, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
+    const dim3 grid((unsigned)((n2 + g->tx - 1) / g->tx), (unsigned)((n1 + ty - 1) / ty), (unsigned)n0);
+    if (grid.y > 65535u || grid.z > 65535u) return -2;
+    lbmk_kernel_%(name)s<<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
         (const %(tin)s*)fin, (%(tout)s*)fout, *g%(peer_arg)s%(scalar_args)s);
     return -(int)cudaGetLastError();
 }
