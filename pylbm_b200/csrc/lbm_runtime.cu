@@ -448,6 +448,7 @@ struct lbm_sim {
     // direct NVLink halo (CUDA IPC): peer arrays [side lo/hi][buffer A/B], arrival counters
     int peers_ready = 0;
     long long signals = 0, waits = 0;             // enqueued so far (host-side bookkeeping)
+    int waited = 0;                               // the wait for the current f was already enqueued
     void* buf[2] = {nullptr, nullptr};            // my arrays A (= desc.f) and B (= desc.fnew)
     void* peer_buf[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     long long peer_pstride[2] = {0, 0};
@@ -458,7 +459,7 @@ struct lbm_sim {
     int use_graph = 0;
     cudaGraphExec_t graph = nullptr;
     void* graph_f = nullptr;
-    int graph_fresh = 0;
+    long long graph_signals = 0;
     int64_t graph_launches = 0;
     // optional per-launch timing of the fused kernel (CUDA events on the launch stream)
     // ghost layers of `f` already hold the periodic images (written by the previous fused launch)
@@ -530,6 +531,14 @@ extern "C" void lbm_sim_destroy(lbm_sim* s) {
     cudaStreamSynchronize(s->stream);
     cudaStreamSynchronize(s->comm_stream);
     if (s->graph) cudaGraphExecDestroy(s->graph);
+    if (s->peers_ready) {
+        const int nsides = (s->nranks == 2) ? 1 : 2;
+        for (int side = 0; side < nsides; ++side) {
+            for (int i = 0; i < 2; ++i) if (s->peer_buf[side][i]) cudaIpcCloseMemHandle(s->peer_buf[side][i]);
+            if (s->peer_flags[side]) cudaIpcCloseMemHandle(s->peer_flags[side]);
+        }
+    }
+    cudaFree(s->flags);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (auto& b : s->bcs) free_bc(b);
     cudaFree(s->scratch);
@@ -606,8 +615,13 @@ extern "C" int lbm_sim_set_rhs(lbm_sim* s, int ibc, const double* rhs_host) {
 
 extern "C" int lbm_sim_set_scalars(lbm_sim* s, const double* scalars, int n) {
     if (!s || n < 0 || n > 32 || (n > 0 && !scalars)) return ARG_ERROR("lbm_sim_set_scalars");
-    for (int i = 0; i < n; ++i) s->d.scalars[i] = scalars[i];
+    bool changed = (n != s->d.nscalars);
+    for (int i = 0; i < n; ++i) {
+        if (s->d.scalars[i] != scalars[i]) changed = true;
+        s->d.scalars[i] = scalars[i];
+    }
     s->d.nscalars = n;
+    if (changed) drop_graph(s);   // kernel arguments are baked into the captured graph
     return 0;
 }
 
@@ -668,10 +682,14 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
     if (s->nranks > 1) {
         if (s->peers_ready && s->ghost_fresh) {
             // the neighbours stored their slab-face images into my ghost planes during their previous
-            // fused kernel: just wait for both of them to have finished it
-            k_wait<<<1, 32, 0, st>>>(s->flags);
-            s->launches += 1;
-            s->waits += 1;
+            // fused kernel: just wait for both of them to have finished it (once per array state:
+            // lbm_sim_boundary_condition may already have done it)
+            if (!s->waited) {
+                k_wait<<<1, 32, 0, st>>>(s->flags);
+                s->launches += 1;
+                s->waits += 1;
+                s->waited = 1;
+            }
         } else {
             int rc = exchange_slabs(s, f, st);
             if (rc) return rc;
@@ -734,6 +752,7 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
         k_signal<<<1, 32, 0, st>>>(s->peer_flags[0] + 1, s->peer_flags[1] + 0);
         s->launches += 1;
         s->signals += 1;
+        s->waited = 0;
     }
     s->ghost_fresh = 1;   // fnew (the next f) now carries its periodic images
     return 0;
@@ -743,20 +762,23 @@ static int build_graph(lbm_sim* s) {
     drop_graph(s);
     cudaGraph_t graph = nullptr;
     const int64_t before = s->launches;
-    const int fresh_at_capture = s->ghost_fresh;
+    const long long sig_before = s->signals, wait_before = s->waits;
     CUDA_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
     int rc = one_step(s, s->f, s->fnew, s->t, s->stream);
     if (rc == 0) rc = one_step(s, s->fnew, s->f, s->t, s->stream);
     cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
     s->graph_launches = s->launches - before;
+    s->graph_signals = s->signals - sig_before;
     s->launches = before;
+    s->signals = sig_before;      // nothing was executed during the capture
+    s->waits = wait_before;
+    s->waited = 0;
     if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return set_error(-(int)e, "cudaStreamEndCapture", cudaGetErrorString(e));
     e = cudaGraphInstantiate(&s->graph, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return set_error(-(int)e, "cudaGraphInstantiate", cudaGetErrorString(e));
     s->graph_f = s->f;
-    s->graph_fresh = fresh_at_capture;
     return 0;
 }
 
@@ -764,33 +786,29 @@ extern "C" int lbm_sim_step(lbm_sim* s, int nsteps) {
     if (!s || nsteps < 0) return ARG_ERROR("lbm_sim_step");
     int done = 0;
     const bool graph_ok = s->use_graph && s->d.t_index < 0 && (s->nranks == 1 || s->peers_ready) && !s->profile;
-    if (graph_ok && nsteps >= 3 && !s->ghost_fresh && s->wrap_mask) {
-        // first step refreshes the ghosts with the copy kernels; the captured pairs then skip them
-        int rc = one_step(s, s->f, s->fnew, s->t, s->stream);
-        if (rc) return rc;
-        void* tmp = s->f; s->f = s->fnew; s->fnew = tmp;
-        s->t += s->d.dt;
-        s->nt += 1;
-        done = 1;
-    }
-    if (graph_ok && nsteps - done >= 2) {
-        if (!s->graph || s->graph_f != s->f || s->graph_fresh != s->ghost_fresh) {
-            int rc = build_graph(s);
-            if (rc) return rc;
-        }
-        for (; done + 2 <= nsteps; done += 2) {
+    while (done < nsteps) {
+        // pairs of steps (f -> fnew -> f) are replayed from a CUDA graph once the ghost layers are
+        // maintained by the fused kernel itself (no copy kernels / NCCL calls inside the capture)
+        if (graph_ok && s->ghost_fresh && !s->waited && nsteps - done >= 2) {
+            if (!s->graph || s->graph_f != s->f) {
+                int rc = build_graph(s);
+                if (rc) return rc;
+            }
             CUDA_TRY(cudaGraphLaunch(s->graph, s->stream));
             s->launches += s->graph_launches;
+            s->signals += s->graph_signals;
+            s->waits += s->graph_signals;
             s->t += 2 * s->d.dt;
             s->nt += 2;
+            done += 2;
+            continue;
         }
-    }
-    for (; done < nsteps; ++done) {
         int rc = one_step(s, s->f, s->fnew, s->t, s->stream);
         if (rc) return rc;
         void* tmp = s->f; s->f = s->fnew; s->fnew = tmp;
         s->t += s->d.dt;
         s->nt += 1;
+        done += 1;
     }
     return 0;
 }

@@ -127,8 +127,11 @@ class Simulation:
                 "pylbm_b200 only provides generator='cuda' (got %r); there is no CPU fallback" % generator
             )
         rt.ensure_gpu()
-        storage = {"float64": "f64", "f64": "f64", "float32": "f32", "f32": "f32"}[str(np.dtype(dtype))
-                                                                               if not isinstance(dtype, str) else dtype]
+        try:
+            storage = {"float64": "f64", "f64": "f64", "float32": "f32", "f32": "f32"}[
+                dtype if isinstance(dtype, str) else str(np.dtype(dtype))]
+        except KeyError:
+            raise ValueError("dtype must be float64 or float32 (storage of the populations), got %r" % (dtype,))
         self.storage = storage
 
         rank, nranks = slab if slab is not None else (0, 1)

@@ -25,8 +25,11 @@ def _worker(rank, world, nccl_id, case, kw, nsteps, queue, halo, shared, barrier
     sim = pylbm_b200.Simulation(cases.CASES[case](perturb=cases.WAVE, **kw), slab=(rank, world), nccl_id=nccl_id,
                                 gather=gather if halo == "peer" else None)
     sim.run(7)              # graph pairs + single steps
+    sim.boundary_condition()   # consumes the neighbours' signal once; the next step must not wait again
     for _ in range(3):
         sim.one_time_step()
+    sim.boundary_condition()
+    sim.boundary_condition()
     sim.F_halo[0] = sim.F_halo[0]   # outside write: ghosts invalidated, next step exchanges again
     sim.run(nsteps - 10)
     out = {str(k): sim.m[k].copy() for k in sim.scheme.consm}
