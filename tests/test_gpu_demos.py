@@ -1,0 +1,59 @@
+"""
+The reference's own demo regression suite replayed on the CUDA path (reference:
+tests/test_demo_1d.py:14-72, test_demo_2d.py:10-67, test_demo_3d.py:9-33): every dictionary a
+reference demo hands to `pylbm.Simulation` is handed UNCHANGED (generator='cuda') to
+`pylbm_b200.Simulation`, stepped with the demos' loop `while sol.t < Tf: sol.one_time_step()` and
+compared at the final time with the reference's golden HDF5 fields and with the fields of the
+unmodified reference (Cython generator) run in the build container -- tests/golden/demos/, made by
+tools/capture_demos.py.  Tolerance: 1e-12 relative to max|field| (north-star bound for fp64; the
+reference's own h5diff tolerance is atol 1e-7 / rtol 1e-14).
+"""
+import numpy as np
+import pytest
+
+from demo_fixtures import demo_names, final_fields, load_demo, load_results, run_to_final_time
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("test", demo_names())
+def test_cuda_reproduces_reference_demo(test):
+    import pylbm_b200
+
+    dico, kwargs, record = load_demo(test)
+    expected = load_results(test)
+    sim = pylbm_b200.Simulation(dico, **kwargs)
+    run_to_final_time(sim, record["final_time"])
+    assert sim.nt == expected["nsteps"]
+    got = final_fields(sim, expected["plane_stride"])
+    assert sorted(got) == sorted(expected["ref"])
+    # 1e-12 is the bound for runs of ~100 steps; the Kelvin-Helmholtz shear layer is
+    # stepped 555 times and amplifies rounding differences (the reference's own run differs from its
+    # golden file by 2.7e-13 there), so the bound grows with the number of steps beyond 100
+    tol = TOL * max(1.0, expected["nsteps"] / 100.0)
+    for kind in ("ref", "h5"):
+        fields = expected[kind]
+        if fields is None:
+            continue
+        for key, want in fields.items():
+            scale = max(np.abs(want).max(), 1e-300)
+            err = np.abs(got[key] - want).max() / scale
+            assert err <= tol, (test, kind, key, err)
+
+
+@pytest.mark.parametrize("test", ["test2D_karman_vortex_street", "test2D_rayleigh_benard", "test3D_poseuille"])
+def test_cuda_run_matches_stepwise(test):
+    """`run(n)` (one runtime call, CUDA-graph pairs) gives the same state as n x one_time_step()."""
+    import pylbm_b200
+
+    dico, kwargs, record = load_demo(test)
+    a = pylbm_b200.Simulation(dico, **kwargs)
+    dico, kwargs, record = load_demo(test)
+    b = pylbm_b200.Simulation(dico, **kwargs)
+    n = load_results(test)["nsteps"]
+    for _ in range(n):
+        a.one_time_step()
+    b.run(n)
+    for key in a.scheme.consm:
+        assert np.array_equal(a.m[key], b.m[key]), (test, str(key))

@@ -1,0 +1,47 @@
+"""
+The reference's own demo regression suite (reference: tests/test_demo_1d.py:14-72,
+test_demo_2d.py:10-67, test_demo_3d.py:9-33) replayed on the ORACLE: the dictionary every reference
+demo hands to `pylbm.Simulation` (captured by tools/capture_demos.py, dx = 1/64, Tf = 0.5) goes
+through the host front-end of the package and the CPU restatement, and the conserved moments at the
+final time are compared with
+
+* the reference's golden HDF5 fields (tests/reference/<test>.h5; the reference's own tolerance is
+  atol 1e-7 / rtol 1e-14, tests/conftest.py:306-307 -- we ask for 1e-12 relative to max|field|);
+* the fields of the unmodified reference run in the build container (also covers the two 3-D
+  tests whose golden files are missing from the reference checkout).
+
+CPU only: this pins the oracle and the front-end on every scheme family / boundary method / source
+term / initialisation mode the reference demos use.
+"""
+import numpy as np
+import pytest
+
+from demo_fixtures import demo_names, final_fields, load_demo, load_results, run_to_final_time
+
+TOL = 1e-12
+
+
+@pytest.mark.parametrize("test", demo_names())
+def test_oracle_reproduces_reference_demo(test):
+    from oracle.lbm_oracle import OracleSimulation
+
+    dico, kwargs, record = load_demo(test)
+    expected = load_results(test)
+    sim = OracleSimulation(dico)
+    assert abs(sim.domain.dx - record["space_step"]) < 1e-15
+    run_to_final_time(sim, record["final_time"])
+    assert sim.nt == expected["nsteps"]
+    got = final_fields(sim, expected["plane_stride"])
+    assert sorted(got) == sorted(expected["ref"])
+    # 1e-12 is the bound for runs of ~100 steps; the Kelvin-Helmholtz shear layer is
+    # stepped 555 times and amplifies rounding differences (the reference's own run differs from its
+    # golden file by 2.7e-13 there), so the bound grows with the number of steps beyond 100
+    tol = TOL * max(1.0, expected["nsteps"] / 100.0)
+    for kind in ("ref", "h5"):
+        fields = expected[kind]
+        if fields is None:
+            continue
+        for key, want in fields.items():
+            scale = max(np.abs(want).max(), 1e-300)
+            err = np.abs(got[key] - want).max() / scale
+            assert err <= tol, (test, kind, key, err)
