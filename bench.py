@@ -205,7 +205,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--dtype", default="float64", choices=["float64", "float32"])
+    ap.add_argument("--dtype", default="float64", choices=["float64", "float32"],
+                    help="storage type of the populations in HBM")
+    ap.add_argument("--compute", default=None, choices=["float64", "float32"],
+                    help="arithmetic type of the time-step kernel (default float64; float32 needs --dtype float32)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
@@ -223,6 +226,7 @@ def main():
     q_of = {"lid_cavity_d3q19": 19, "karman_d2q9": 9, "shallow_water_d2q4": 12, "lid_cavity_d2q9": 9,
             "channel_sphere_d3q27": 27}
     config = {"workload": description, "case": case_name, **case_kw, "storage": args.dtype,
+              "arithmetic": args.compute or "float64",
               "l2": "working set (F + Fnew) far larger than the 126 MB L2; no flush needed"}
 
     # ---- reference arm: CPU restatement only, rank 0 alone -----------------
@@ -279,7 +283,7 @@ def main():
             dist.all_gather_object(out, blob)
             return out
     sim = pylbm_b200.Simulation(dico, dtype=args.dtype, slab=(rank, world) if world > 1 else None, nccl_id=nccl_id,
-                                gather=gather)
+                                gather=gather, compute_dtype=args.compute)
     t_build = time.time() - t_build
     global_cells = float(np.prod(sim.domain.global_size))
     local_cells = float(np.prod(sim.domain.shape_in))
@@ -389,7 +393,8 @@ def main():
         line = {
             "metric": "MLUPS", "value": value, "unit": "MLUPS", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": scaling, "vs_baseline": None, "dtype": "f64" if args.dtype == "float64" else "f32-storage/f64-math",
+            "scaling": scaling, "vs_baseline": None, "dtype": ("f64" if args.dtype == "float64" else
+                                                                    ("f32" if args.compute == "float32" else "f32-storage/f64-math")),
             "data": "synthetic", "config": dict(config, parallelism="x-slabs x%d" % world, setup_s=round(t_build, 2),
                            halo=(args.halo if world > 1 else "periodic (single GPU)")),
             "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu, "gpu_launches": int(launches),

@@ -32,6 +32,9 @@ extern "C" {
  * `lead` is chosen so that the first interior cell of every row is 128-byte aligned
  * (replaces the reference's `sorder` permutation of a dense NumPy array,
  * pylbm/storage.py:60-118).  n[] INCLUDES the ghost layers (reference: vmax per side).
+ * pitch, lead and pstride are counted in ELEMENTS and ONE grid describes both the input and the
+ * output array of a launch, whatever their element types (fp32 populations in, fp64 moments out):
+ * arrays that meet in a kernel are allocated with the same element layout.
  */
 typedef struct {
     int n[3];         /* halo-inclusive logical sizes, slowest .. fastest            */

@@ -32,38 +32,47 @@ ABI_VERSION = 1
 
 
 class CudaPrinter(C99CodePrinter):
-    """C printer for double arithmetic: integer powers as products, reciprocal
-    as 1.0/x, rationals and floats as round-trip double literals."""
+    """C printer for the per-cell arithmetic: integer powers as products, reciprocal as 1.0/x,
+    rationals and floats as round-trip double literals (`single=True`: float literals, the decimal
+    text of the double followed by `f`, and the float math functions)."""
+
+    def __init__(self, single=False):
+        super().__init__()
+        self._sfx = "f" if single else ""
+
+    def _literal(self, value):
+        text = repr(float(value)) + self._sfx
+        return text if float(value) >= 0 else "(%s)" % text
 
     def _print_Rational(self, expr):
-        return repr(float(sp.Float(expr, 30)))
+        return self._literal(float(sp.Float(expr, 30)))
 
     def _print_Integer(self, expr):
-        return "%d.0" % int(expr) if int(expr) >= 0 else "(%d.0)" % int(expr)
+        return self._literal(int(expr))
 
     def _print_Float(self, expr):
-        val = repr(float(expr))
-        return val if float(expr) >= 0 else "(%s)" % val
+        return self._literal(float(expr))
 
     def _print_Pow(self, expr):
         base, exp = expr.base, expr.exp
+        one = "1.0" + self._sfx
         if exp.is_Integer:
             n = int(exp)
             b = self.parenthesize(base, 1000)
             if n == -1:
-                return "(1.0/%s)" % b
+                return "(%s/%s)" % (one, b)
             if 0 < n <= 8:
                 return "(" + "*".join([b] * n) + ")"
             if -8 <= n < 0:
-                return "(1.0/(" + "*".join([b] * (-n)) + "))"
+                return "(%s/(" % one + "*".join([b] * (-n)) + "))"
         if exp == sp.Rational(1, 2):
-            return "sqrt(%s)" % self._print(base)
+            return "sqrt%s(%s)" % (self._sfx, self._print(base))
         if exp == sp.Rational(-1, 2):
-            return "rsqrt(%s)" % self._print(base)
-        return "pow(%s, %s)" % (self._print(base), self._print(exp))
+            return "rsqrt%s(%s)" % (self._sfx, self._print(base))
+        return "pow%s(%s, %s)" % (self._sfx, self._print(base), self._print(exp))
 
 
-_printer = CudaPrinter()
+_printers = {False: CudaPrinter(False), True: CudaPrinter(True)}
 
 
 def _to_exact(expr):
@@ -197,6 +206,12 @@ typedef struct {
     int nin_lo;          // interior size of the `lo` neighbour along the slab axis
 } lbmk_peers;
 }
+typedef struct {       // per-axis description of the cells that own a periodic / neighbour image
+    int below[3];      // index <  below: image at +dlow  (in a high ghost layer)
+    int above[3];      // index >= above: image at dhigh (< 0, in a low ghost layer)
+    long long dlow[3];
+    long long dhigh[3];
+} lbmk_images;
 #define SLAB %(slab)d
 
 typedef %(storage)s real_f;   // storage type of the populations in HBM
@@ -208,9 +223,16 @@ _KERNEL = r"""
 // ---------------------------------------------------------------------------
 // %(name)s : %(nin)d loads, %(nout)d stores per cell; %(ops)s
 // ---------------------------------------------------------------------------
+// byte offsets of the loads / stores relative to the cell, one per population: computed on the
+// host by the launcher and read from the kernel-parameter constant bank, so that an access costs
+// one 64-bit add (2 instructions) instead of re-deriving k*pstride + neighbour offset per thread
+struct lbmk_offs_%(name)s { long long in[%(nin)d]; long long out[%(nout)d]; };
+
 __global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
-lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g%(peer_param)s%(scalar_params)s)
+lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g,
+    const lbmk_offs_%(name)s offs%(peer_param)s%(scalar_params)s)
 {
+    typedef %(tc)s real_c;   // arithmetic type of this kernel
     // 3-D grid: x = chunk of the fastest axis, y = group of `ty` rows of axis 1, z = index of axis 0
     // (no integer division in the prologue; tx is a power of two)
     const unsigned tid = threadIdx.x;
@@ -224,6 +246,10 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
     const long long rowstride = g.pitch;
     const long long planestride = (long long)g.n[1] * g.pitch;
     const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
+    (void)rowstride; (void)planestride;
+    unsigned long long pin = (unsigned long long)(fin + cell);
+    unsigned long long pout = (unsigned long long)(fout + cell);
+    asm volatile("" : "+l"(pin), "+l"(pout));   // keep `pointer + constant-bank offset` as the address form
 %(loads)s
 %(prologue)s
 %(body)s
@@ -239,8 +265,15 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
     const int ty = LBMK_BLOCK / g->tx;
     const dim3 grid((unsigned)((n2 + g->tx - 1) / g->tx), (unsigned)((n1 + ty - 1) / ty), (unsigned)n0);
     if (grid.y > 65535u || grid.z > 65535u) return -2;
-    lbmk_kernel_%(name)s<<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
-        (const %(tin)s*)fin, (%(tout)s*)fout, *g%(peer_arg)s%(scalar_args)s);
+    static const int noff[%(nin)d][3] = {%(offset_table)s};
+    lbmk_offs_%(name)s offs;
+    const long long plane = (long long)g->n[1] * g->pitch;
+    for (int k = 0; k < %(nin)d; ++k)
+        offs.in[k] = (k * g->pstride + noff[k][0] * plane + noff[k][1] * g->pitch + noff[k][2]) * (long long)sizeof(%(tin)s);
+    for (int k = 0; k < %(nout)d; ++k)
+        offs.out[k] = k * g->pstride * (long long)sizeof(%(tout)s);
+%(images_launch)s    lbmk_kernel_%(name)s<<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
+        (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs%(peer_arg)s%(scalar_args)s);
     return -(int)cudaGetLastError();
 }
 %(launch_tail)s"""
@@ -256,31 +289,41 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
 # every axis of A.  Only those (population, image) pairs are stored; the other ghost entries are
 # scratch (they are also never refreshed in the reference's Fnew, simulation.py:417).
 _IMAGES_PROLOGUE = r"""    // ---- periodic / neighbour images of this cell (see the comment above _IMAGES_PROLOGUE) ----
-    long long d0 = 0, d1 = 0, d2 = 0;    // offset of the image along each axis (0: none)
-    %(tout)s* qbase = fout;              // array receiving the images that cross the SLAB axis
+    // offset of the image along each axis (0: none); thresholds and offsets come precomputed from
+    // the launcher (an inactive axis has thresholds that never match)
+    const long long d0 = i0 < img.below[0] ? img.dlow[0] : (i0 >= img.above[0] ? img.dhigh[0] : 0LL);
+    const long long d1 = i1 < img.below[1] ? img.dlow[1] : (i1 >= img.above[1] ? img.dhigh[1] : 0LL);
+    const long long d2 = i2 < img.below[2] ? img.dlow[2] : (i2 >= img.above[2] ? img.dhigh[2] : 0LL);
+    // array receiving the images that cross the SLAB axis (a neighbour's array with the peer halo)
+    %(tout)s* qbase = fout;
     long long qps = g.pstride;
-    if (g.wrap | (pr.lo != nullptr)) {
-        const long long stride_[3] = {planestride, rowstride, 1};
-        const int idx_[3] = {i0, i1, i2};
-        long long d_[3] = {0, 0, 0};
-#pragma unroll
-        for (int a_ = 0; a_ < 3; ++a_) {
-            const bool peer_ = (a_ == SLAB) && pr.lo != nullptr;
-            if (!(((g.wrap >> a_) & 1) || peer_) || g.w[a_] <= 0) continue;
-            const int nin = g.n[a_] - 2 * g.w[a_];
-            if (idx_[a_] < 2 * g.w[a_]) {            // near the low face: image in a HIGH ghost layer
-                d_[a_] = (long long)(peer_ ? pr.nin_lo : nin) * stride_[a_];
-                if (peer_) { qbase = (%(tout)s*)pr.lo; qps = pr.pstride_lo; }
-            } else if (idx_[a_] >= nin) {            // near the high face: image in a LOW ghost layer
-                d_[a_] = -(long long)nin * stride_[a_];
-                if (peer_) { qbase = (%(tout)s*)pr.hi; qps = pr.pstride_hi; }
-            }
-        }
-        d0 = d_[0]; d1 = d_[1]; d2 = d_[2];
+    if (pr.lo != nullptr) {
+        const long long ds_ = (SLAB == 0) ? d0 : ((SLAB == 1) ? d1 : d2);
+        if (ds_ > 0) { qbase = (%(tout)s*)pr.lo; qps = pr.pstride_lo; }
+        else if (ds_ < 0) { qbase = (%(tout)s*)pr.hi; qps = pr.pstride_hi; }
     }
     // an image in a HIGH ghost layer (d > 0) is read by populations moving in -axis, and vice versa
     const bool p0 = d0 < 0, m0 = d0 > 0, p1 = d1 < 0, m1 = d1 > 0, p2 = d2 < 0, m2 = d2 > 0;
     (void)p0; (void)m0; (void)p1; (void)m1; (void)p2; (void)m2; (void)qbase; (void)qps;
+"""
+
+# launcher side of the above: per axis, cells with index < below have an image in the HIGH ghost
+# layer at +dlow, cells with index >= above have one in the LOW ghost layer at dhigh (< 0)
+_IMAGES_LAUNCH = r"""
+    lbmk_images img;
+    {
+        const lbmk_peers* pp = peers;
+        const long long stride_[3] = {(long long)g->n[1] * g->pitch, g->pitch, 1};
+        for (int a = 0; a < 3; ++a) {
+            const bool peer_ = (a == SLAB) && pp && pp->lo != nullptr;
+            const bool on = ((((g->wrap >> a) & 1) != 0) || peer_) && g->w[a] > 0;
+            const int nin = g->n[a] - 2 * g->w[a];
+            img.below[a] = on ? 2 * g->w[a] : -2147483647 - 1;
+            img.above[a] = on ? nin : 2147483647;
+            img.dlow[a] = on ? (long long)(peer_ ? pp->nin_lo : nin) * stride_[a] : 0;
+            img.dhigh[a] = on ? -(long long)nin * stride_[a] : 0;
+        }
+    }
 """
 
 
@@ -292,7 +335,7 @@ def _inline_image(v, k, slab):
     cond = "p2" if v[2] > 0 else "m2"
     if slab == 2:
         return " if (%s) qbase[%dLL * qps + cell + d2] = o_;" % (cond, k)
-    return " if (%s) p_[d2] = o_;" % cond
+    return " if (%s) __stcg(p_ + d2, o_);" % cond
 
 
 def _images_code(velocities, tout, slab):
@@ -325,19 +368,6 @@ def _images_code(velocities, tout, slab):
     return "\n".join(lines)
 
 
-def _offset_expr(off):
-    """element offset of a neighbour for canonical 3-D integer offset."""
-    terms = []
-    o0, o1, o2 = off
-    if o0:
-        terms.append("%d * planestride" % o0)
-    if o1:
-        terms.append("%d * rowstride" % o1)
-    if o2:
-        terms.append("%d" % o2)
-    return " + ".join(terms) if terms else "0"
-
-
 def _canonical(offset):
     offset = tuple(int(o) for o in offset)
     return (0,) * (3 - len(offset)) + offset
@@ -354,48 +384,52 @@ extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, co
 """
 
 
-def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0):
+def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0, compute="double"):
+    """CUDA source of one per-cell kernel + its C-ABI launcher.  `compute` is the arithmetic type of
+    the kernel body (double, or float for the all-fp32 mode of the fused kernel)."""
     temps, outs = lower_statements(ir.statements, ir.outputs, cse=cse)
+    pr = _printers[compute == "float"]
     nq = len(ir.in_syms)
     tin = "real_m" if ir.in_array == "m" else "real_f"
     tout = "real_m" if ir.out_array == "m" else "real_f"
     loads = []
-    for k, (sym, off) in enumerate(zip(ir.in_syms, ir.in_offsets)):
-        loads.append(
-            "    const double %s = (double)__ldg(fin + (%d * g.pstride + cell + (%s)));"
-            % (sym, k, _offset_expr(_canonical(off)))
-        )
-    body = ["    const double %s = %s;" % (lhs, _printer.doprint(rhs)) for lhs, rhs in temps]
+    for k, sym in enumerate(ir.in_syms):
+        loads.append("    const real_c %s = (real_c)__ldg((const %s*)(pin + offs.in[%d]));" % (sym, tin, k))
+    body = ["    const real_c %s = %s;" % (lhs, pr.doprint(rhs)) for lhs, rhs in temps]
     if images:
         vels = [tuple(-o for o in _canonical(off)) for off in ir.in_offsets]
         stores = [
-            "    { const %s o_ = (%s)(%s); %s* p_ = fout + (%dLL * g.pstride + cell); *p_ = o_;%s }"
-            % (tout, tout, _printer.doprint(o), tout, k, _inline_image(vels[k], k, slab))
+            "    { const %s o_ = (%s)(%s); %s* p_ = (%s*)(pout + offs.out[%d]); __stcg(p_, o_);%s }"
+            % (tout, tout, pr.doprint(o), tout, tout, k, _inline_image(vels[k], k, slab))
             for k, o in enumerate(outs)
         ]
     else:
         stores = [
-            "    fout[%d * g.pstride + cell] = (%s)(%s);" % (k, tout, _printer.doprint(o))
+            "    __stcg((%s*)(pout + offs.out[%d]), (%s)(%s));" % (tout, k, tout, pr.doprint(o))
             for k, o in enumerate(outs)
         ]
     add, mul, div = count_ops(temps, outs)
-    scal_params = "".join(", const double %s" % _c_name(s) for s in ir.scalars)
-    scal_args = "".join(", scalars[%d]" % i for i in range(len(ir.scalars)))
-    src = _KERNEL % dict(
+    scal_params = "".join(", const real_c_%s %s" % (ir.name, _c_name(s)) for s in ir.scalars)
+    scal_args = "".join(", (real_c_%s)scalars[%d]" % (ir.name, i) for i in range(len(ir.scalars)))
+    table = ", ".join("{%d, %d, %d}" % _canonical(off) for off in ir.in_offsets)
+    src = "typedef %s real_c_%s;\n" % (compute, ir.name) + _KERNEL % dict(
         name=ir.name,
         tin=tin,
         tout=tout,
+        tc=compute,
         nin=nq,
         nout=len(outs),
-        ops="%d add, %d mul, %d div before FMA contraction" % (add, mul, div),
+        ops="%d add, %d mul, %d div before FMA contraction, %s arithmetic" % (add, mul, div, compute),
         minblocks=minblocks,
         scalar_params=scal_params,
         scalar_args=scal_args,
+        offset_table=table,
         loads="\n".join(loads),
         images=_images_code([tuple(-o for o in _canonical(off)) for off in ir.in_offsets], tout, slab) if images else "",
         prologue=(_IMAGES_PROLOGUE % dict(tout=tout)) if images else "",
-        peer_param=", const lbmk_peers pr" if images else "",
-        peer_arg=", (peers ? *peers : lbmk_peers{nullptr, nullptr, 0, 0, 0})" if images else "",
+        peer_param=", const lbmk_peers pr, const lbmk_images img" if images else "",
+        peer_arg=", (peers ? *peers : lbmk_peers{nullptr, nullptr, 0, 0, 0}), img" if images else "",
+        images_launch=_IMAGES_LAUNCH if images else "",
         launch_head=(_LAUNCH_HEAD_PEERS if images else _LAUNCH_HEAD) % dict(name=ir.name),
         launch_tail=(_LAUNCH_TAIL_PEERS % dict(name=ir.name)) if images else "",
         body="\n".join(body),
@@ -408,7 +442,8 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
     return src, (add, mul, div)
 
 
-_C_KEYWORDS = {"lambda", "double", "int", "float", "long", "short", "register", "const", "void", "auto", "g", "fin", "fout", "cell", "tid"}
+_C_KEYWORDS = {"lambda", "double", "int", "float", "long", "short", "register", "const", "void", "auto", "g", "fin", "fout", "cell", "tid",
+               "pin", "pout", "offs", "pr", "tx", "ty", "i0", "i1", "i2", "d0", "d1", "d2", "real_c"}
 
 
 def _c_name(name):
@@ -445,7 +480,7 @@ def default_minblocks(nv):
     return 5
 
 
-def kernel_tag(kernels, dim, nv, storage="double", cse=True):
+def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):
     """
     Cache key of a kernel library: hash of the IR (deterministic across processes, unlike the text
     produced by sympy.cse whose temporaries depend on set ordering), of the generator options and
@@ -454,7 +489,7 @@ def kernel_tag(kernels, dim, nv, storage="double", cse=True):
     h = hashlib.sha256()
     with open(__file__.replace(".pyc", ".py"), "rb") as fh:
         h.update(fh.read())
-    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv))).encode())
+    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv), compute)).encode())
     for ir in kernels:
         h.update(repr((ir.name, ir.in_array, ir.out_array, bool(ir.inner), list(ir.scalars),
                        [str(s) for s in ir.in_syms], [tuple(o) for o in ir.in_offsets])).encode())
@@ -465,18 +500,24 @@ def kernel_tag(kernels, dim, nv, storage="double", cse=True):
     return h.hexdigest()[:20]
 
 
-def generate_source(kernels, dim, nv, storage="double", cse=True):
+def generate_source(kernels, dim, nv, storage="double", cse=True, compute="double"):
     """
     Full translation unit for a list of KernelIR.  Returns (source, info dict).
+    `storage` is the type of the populations in HBM, `compute` the arithmetic type of the
+    time-step kernels (one_time_step, transport); the whole-array kernels that produce or consume
+    moments (f2m, m2f, equilibrium, ...) always compute in double.
     """
+    if compute == "float" and storage != "float":
+        raise ValueError("float arithmetic needs float storage of the populations")
     import json
 
     parts = [_HEADER % dict(abi=ABI_VERSION, storage=storage, slab=3 - dim)]
-    info = {"abi": ABI_VERSION, "dim": dim, "nv": nv, "storage": storage, "routines": {}}
+    info = {"abi": ABI_VERSION, "dim": dim, "nv": nv, "storage": storage, "compute": compute, "routines": {}}
     for ir in kernels:
         fused = ir.name == "one_time_step"
         src, ops = kernel_source(ir, storage=storage, cse=cse, images=fused,
-                                 minblocks=default_minblocks(nv) if fused else 1, slab=3 - dim)
+                                 minblocks=default_minblocks(nv) if fused else 1, slab=3 - dim,
+                                 compute=compute if ir.name in ("one_time_step", "transport") else "double")
         parts.append(src)
         info["routines"][ir.name] = {
             "scalars": list(ir.scalars),
@@ -489,5 +530,5 @@ def generate_source(kernels, dim, nv, storage="double", cse=True):
     literal = '"' + text.replace("\\", "\\\\").replace('"', '\\"') + '"'
     parts.append(_DESCRIBE % dict(json=literal))
     source = "\n".join(parts)
-    info["hash"] = kernel_tag(kernels, dim, nv, storage, cse)
+    info["hash"] = kernel_tag(kernels, dim, nv, storage, cse, compute)
     return source, info

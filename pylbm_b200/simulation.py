@@ -37,7 +37,7 @@ from .storage import DeviceArray
 __all__ = ["Simulation", "CudaContainer"]
 
 
-def build_kernel_library(scheme, settings=None, storage="f64", need_source=False):
+def build_kernel_library(scheme, settings=None, storage="f64", need_source=False, compute="f64"):
     """
     scheme -> per-cell kernel IR -> CUDA C -> liblbmk_<hash>.so (cached in-tree by source hash).
     Needs nvcc but no GPU, so it is also what `__graft_entry__.build()` runs on the build box.
@@ -47,11 +47,12 @@ def build_kernel_library(scheme, settings=None, storage="f64", need_source=False
     algo_settings.update(settings or {})
     algo = PullAlgorithm(scheme, algo_settings)
     c_storage = "double" if storage == "f64" else "float"
+    c_compute = "double" if compute == "f64" else "float"
     kernels = algo.kernels()
-    path = build.kernel_library_path(kernel_tag(kernels, scheme.dim, algo.ns, storage=c_storage))
+    path = build.kernel_library_path(kernel_tag(kernels, scheme.dim, algo.ns, storage=c_storage, compute=c_compute))
     if os.path.exists(path) and not need_source:
         return algo, path, None          # cached: no lowering, no nvcc
-    source, info = generate_source(kernels, scheme.dim, algo.ns, storage=c_storage)
+    source, info = generate_source(kernels, scheme.dim, algo.ns, storage=c_storage, compute=c_compute)
     return algo, build.build_kernels(source, info["hash"]), source
 
 
@@ -95,7 +96,8 @@ class CudaContainer:
     def m(self):
         # moments are only materialised when somebody asks for them
         if self._m is None:
-            self._m = DeviceArray(self.nv, self._shape, self.vmax, "f64", self._consm)
+            # same element layout as F (one lbmk_grid addresses both in f2m / m2f)
+            self._m = DeviceArray(self.nv, self._shape, self.vmax, "f64", self._consm, align=self.F.align)
         return self._m
 
     def release_m(self):
@@ -106,13 +108,16 @@ class CudaContainer:
 class Simulation:
     """
     Simulation(dico, sorder=None, dtype='float64', check_inverse=False, initialize=True,
-               slab=None, nccl_id=None)
+               slab=None, nccl_id=None, gather=None, compute_dtype=None)
 
     `dico` is a pylbm dictionary (box, elements, space_step, scheme_velocity, schemes,
     parameters, relative_velocity, init, inittype, boundary_conditions, generator,
     codegen_option, lbm_algorithm, show_code).  `dtype='float32'` selects fp32 STORAGE of
     the populations (arithmetic stays fp64) -- new functionality, the reference ignores
-    its dtype argument (simulation.py:89-91, storage.py:67).
+    its dtype argument (simulation.py:89-91, storage.py:67).  `compute_dtype='float32'` (only with
+    dtype='float32') also runs the time-step kernels in fp32 arithmetic: the all-single-precision
+    mode, tolerance stated in tests/test_gpu_parity.py; moments (`sol.m`), initialisation and wall
+    equilibria are always computed in fp64.
     `slab=(rank, nranks)` + `nccl_id` run this process as one x-slab of a multi-GPU run (NCCL
     send/recv halo).  `gather(bytes) -> [bytes of every rank]` (an all-gather provided by the caller,
     e.g. torch.distributed.all_gather_object) additionally enables the direct NVLink halo: the fused
@@ -120,7 +125,7 @@ class Simulation:
     """
 
     def __init__(self, dico, sorder=None, dtype="float64", check_inverse=False, initialize=True,
-                 slab=None, nccl_id=None, gather=None):
+                 slab=None, nccl_id=None, gather=None, compute_dtype=None):
         generator = str(dico.get("generator", "cuda")).upper()
         if generator != "CUDA":
             raise ValueError(
@@ -133,6 +138,14 @@ class Simulation:
         except KeyError:
             raise ValueError("dtype must be float64 or float32 (storage of the populations), got %r" % (dtype,))
         self.storage = storage
+        names = {"float64": "f64", "f64": "f64", "float32": "f32", "f32": "f32", None: "f64"}
+        try:
+            compute = names[compute_dtype if isinstance(compute_dtype, (str, type(None))) else str(np.dtype(compute_dtype))]
+        except KeyError:
+            raise ValueError("compute_dtype must be float64 or float32, got %r" % (compute_dtype,))
+        if compute == "f32" and storage != "f32":
+            raise ValueError("compute_dtype='float32' needs dtype='float32' (fp32 storage of the populations)")
+        self.compute = compute
 
         rank, nranks = slab if slab is not None else (0, 1)
         topo = None
@@ -158,7 +171,7 @@ class Simulation:
         codegen_opt = dico.get("codegen_option", None)
         want_source = bool(dico.get("show_code", False) or (codegen_opt and codegen_opt.get("directory")))
         self.algo, lib_path, source = build_kernel_library(self.scheme, user_algo.get("settings", {}), storage,
-                                                           need_source=want_source)
+                                                           need_source=want_source, compute=compute)
         if dico.get("show_code", False):
             print(source)
         if codegen_opt and codegen_opt.get("directory"):
@@ -321,7 +334,7 @@ class Simulation:
         cache = self.__dict__.setdefault("_scratch_arrays", {})
         key = (nv, ncell, storage, slot)
         if key not in cache:
-            cache[key] = DeviceArray(nv, (ncell,), [0], storage)
+            cache[key] = DeviceArray(nv, (ncell,), [0], storage, align=self.container.F.align)
         return cache[key]
 
     def _on_device(self, host):

@@ -71,9 +71,12 @@ class DeviceArray(_ConsmMixin):
     Padded SoA array in HBM.  `nspace` includes the ghost layers (`vmax` per side).
     `storage` is 'f64' (default, the reference's only type: storage.py:67) or 'f32'
     (optional reduced-precision storage, arithmetic stays fp64).
+    `align` = row alignment in ELEMENTS (default: 128 bytes of this array's own type).  A kernel
+    addresses its input and output arrays with ONE lbmk_grid, so arrays of different element types
+    that meet in a kernel (fp32 populations and fp64 moments) must be built with the same `align`.
     """
 
-    def __init__(self, nv, nspace, vmax, storage="f64", consm=None):
+    def __init__(self, nv, nspace, vmax, storage="f64", consm=None, align=None):
         rt.ensure_gpu()
         self.nv = int(nv)
         self.nspace = tuple(int(n) for n in nspace)
@@ -87,7 +90,8 @@ class DeviceArray(_ConsmMixin):
 
         n = (1,) * (3 - self.dim) + self.nspace
         w = (0,) * (3 - self.dim) + tuple(self.vmax)
-        align = 128 // self.itemsize
+        align = int(align) if align else 128 // self.itemsize
+        self.align = align
         pitch = _roundup(n[2], align)
         lead = (align - w[2]) % align
         rows = n[0] * n[1]
