@@ -88,10 +88,13 @@ extern "C" int lbm_memcpy_d2d(void* dst, const void* src, uint64_t bytes) {
 // dense host block <-> padded device array
 // ---------------------------------------------------------------------------
 template <typename S, bool TO_PADDED>
-__global__ void k_repack(S* __restrict__ padded, double* __restrict__ dense, lbmk_grid g, int k0, long long count) {
-    // dense: [nk][n0][n1][n2]; one thread per dense element of ONE population chunk
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
+__global__ void k_repack(S* __restrict__ padded, double* __restrict__ dense, lbmk_grid g, int k0, long long first,
+                         long long count) {
+    // dense: [nk][n0][n1][n2] flattened; this launch handles the dense elements [first, first + count),
+    // staged in dense[0 .. count)
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    const long long i = first + j;
     const long long n2 = g.n[2], n1 = g.n[1];
     const long long per_pop = (long long)g.n[0] * n1 * n2;
     const long long k = i / per_pop;
@@ -100,50 +103,82 @@ __global__ void k_repack(S* __restrict__ padded, double* __restrict__ dense, lbm
     const long long row = r / n2;  // i0*n1 + i1
     const long long pos = (k0 + k) * g.pstride + g.lead + row * g.pitch + i2;
     if (TO_PADDED)
-        padded[pos] = (S)dense[i];
+        padded[pos] = (S)dense[j];
     else
-        dense[i] = (double)padded[pos];
+        dense[j] = (double)padded[pos];
+}
+
+// two staging buffers + two streams per process: the repack kernel of one chunk overlaps the PCIe copy
+// of the other (full speed when the host side is page-locked, e.g. lbm_host_alloc memory)
+struct RepackPipe {
+    int device = -1;
+    double* stage[2] = {nullptr, nullptr};
+    cudaStream_t st[2] = {nullptr, nullptr};
+    long long chunk = 0;   // elements per staging buffer
+};
+static RepackPipe g_pipe;
+
+static int repack_pipe(long long want) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (g_pipe.device == dev && g_pipe.chunk >= want) return 0;
+    for (int b = 0; b < 2; ++b) {
+        if (g_pipe.stage[b]) cudaFree(g_pipe.stage[b]);
+        if (g_pipe.st[b]) cudaStreamDestroy(g_pipe.st[b]);
+        g_pipe.stage[b] = nullptr;
+        g_pipe.st[b] = nullptr;
+    }
+    g_pipe.device = -1;
+    for (int b = 0; b < 2; ++b) {
+        CUDA_TRY(cudaMalloc(&g_pipe.stage[b], (size_t)want * 8));
+        CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.st[b], cudaStreamNonBlocking));
+    }
+    g_pipe.device = dev;
+    g_pipe.chunk = want;
+    return 0;
 }
 
 template <bool TO_PADDED>
 static int repack(void* dev, double* host, const lbmk_grid* g, int storage, int k0, int nk) {
     if (!dev || !host || !g) return ARG_ERROR("null pointer");
     const long long per_pop = (long long)g->n[0] * g->n[1] * g->n[2];
-    // stage through a device buffer of at most ~256 MB
-    long long pops_per_chunk = (256LL << 20) / (per_pop * 8);
-    if (pops_per_chunk < 1) pops_per_chunk = 1;
-    if (pops_per_chunk > nk) pops_per_chunk = nk;
-    double* stage = nullptr;
-    CUDA_TRY(cudaMalloc(&stage, (size_t)(pops_per_chunk * per_pop * 8)));
-    int rc = 0;
-    for (long long k = 0; k < nk && rc == 0; k += pops_per_chunk) {
-        const long long nkc = (nk - k < pops_per_chunk) ? nk - k : pops_per_chunk;
-        const long long count = nkc * per_pop;
+    const long long total = per_pop * nk;
+    if (total <= 0) return 0;
+    const long long chunk = total < (8LL << 20) ? total : (8LL << 20);     // 64 MB of doubles per buffer
+    int rc = repack_pipe(chunk);
+    if (rc) return rc;
+    CUDA_TRY(cudaDeviceSynchronize());        // everything enqueued so far (any stream) has finished
+    cudaError_t e = cudaSuccess;
+    int b = 0;
+    for (long long first = 0; first < total && e == cudaSuccess; first += chunk, b ^= 1) {
+        const long long count = (total - first < chunk) ? total - first : chunk;
         const unsigned blocks = (unsigned)((count + 255) / 256);
-        cudaError_t e = cudaSuccess;
+        cudaStream_t st = g_pipe.st[b];
+        double* stage = g_pipe.stage[b];
         if (TO_PADDED) {
-            e = cudaMemcpy(stage, host + k * per_pop, (size_t)count * 8, cudaMemcpyHostToDevice);
-            if (e == cudaSuccess) {
-                if (storage == LBM_STORAGE_F64)
-                    k_repack<double, true><<<blocks, 256>>>((double*)dev, stage, *g, k0 + (int)k, count);
-                else
-                    k_repack<float, true><<<blocks, 256>>>((float*)dev, stage, *g, k0 + (int)k, count);
-                e = cudaGetLastError();
-            }
-            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            e = cudaMemcpyAsync(stage, host + first, (size_t)count * 8, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) break;
+            if (storage == LBM_STORAGE_F64)
+                k_repack<double, true><<<blocks, 256, 0, st>>>((double*)dev, stage, *g, k0, first, count);
+            else
+                k_repack<float, true><<<blocks, 256, 0, st>>>((float*)dev, stage, *g, k0, first, count);
+            e = cudaGetLastError();
         } else {
             if (storage == LBM_STORAGE_F64)
-                k_repack<double, false><<<blocks, 256>>>((double*)dev, stage, *g, k0 + (int)k, count);
+                k_repack<double, false><<<blocks, 256, 0, st>>>((double*)dev, stage, *g, k0, first, count);
             else
-                k_repack<float, false><<<blocks, 256>>>((float*)dev, stage, *g, k0 + (int)k, count);
+                k_repack<float, false><<<blocks, 256, 0, st>>>((float*)dev, stage, *g, k0, first, count);
             e = cudaGetLastError();
             if (e == cudaSuccess)
-                e = cudaMemcpy(host + k * per_pop, stage, (size_t)count * 8, cudaMemcpyDeviceToHost);
+                e = cudaMemcpyAsync(host + first, stage, (size_t)count * 8, cudaMemcpyDeviceToHost, st);
         }
-        if (e != cudaSuccess) rc = set_error(-(int)e, "lbm_array copy", cudaGetErrorString(e));
     }
-    cudaFree(stage);
-    return rc;
+    for (int i = 0; i < 2; ++i) {
+        cudaError_t e2 = cudaStreamSynchronize(g_pipe.st[i]);
+        if (e == cudaSuccess) e = e2;
+    }
+    if (e != cudaSuccess) return set_error(-(int)e, "lbm_array copy", cudaGetErrorString(e));
+    return 0;
 }
 
 extern "C" int lbm_array_h2d(void* dev, const double* host, const lbmk_grid* g, int storage, int k0, int nk) {

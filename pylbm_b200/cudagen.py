@@ -469,15 +469,17 @@ extern "C" const char* lbmk_describe(void)
 """
 
 
-def default_minblocks(nv):
+def default_minblocks(nv, compute="double"):
     """resident 128-thread blocks per SM requested through __launch_bounds__ for the fused
-    kernel (caps registers: 65536 / (128 * minblocks)); tuned on B200, see DESIGN.md."""
+    kernel (caps registers: 65536 / (128 * minblocks)); tuned on B200, see DESIGN.md:
+    fp64 arithmetic 5 (<= 102 registers; 6 spills), fp32 arithmetic 8 (56 registers; 5 -> 8 gave
+    3.53 -> 3.41 ms on the 512^3 D3Q19 kernel, 10 the same)."""
     import os
 
     env = os.environ.get("PYLBM_B200_MINBLOCKS")
     if env:
         return int(env)
-    return 5
+    return 8 if compute == "float" else 5
 
 
 def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):
@@ -489,7 +491,7 @@ def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):
     h = hashlib.sha256()
     with open(__file__.replace(".pyc", ".py"), "rb") as fh:
         h.update(fh.read())
-    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv), compute)).encode())
+    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv, compute), compute)).encode())
     for ir in kernels:
         h.update(repr((ir.name, ir.in_array, ir.out_array, bool(ir.inner), list(ir.scalars),
                        [str(s) for s in ir.in_syms], [tuple(o) for o in ir.in_offsets])).encode())
@@ -516,7 +518,7 @@ def generate_source(kernels, dim, nv, storage="double", cse=True, compute="doubl
     for ir in kernels:
         fused = ir.name == "one_time_step"
         src, ops = kernel_source(ir, storage=storage, cse=cse, images=fused,
-                                 minblocks=default_minblocks(nv) if fused else 1, slab=3 - dim,
+                                 minblocks=default_minblocks(nv, compute) if fused else 1, slab=3 - dim,
                                  compute=compute if ir.name in ("one_time_step", "transport") else "double")
         parts.append(src)
         info["routines"][ir.name] = {

@@ -152,6 +152,43 @@ def ensure_gpu():
     return n
 
 
+class _PinnedBlock:
+    """page-locked host memory exposed through the array interface; freed with the last view."""
+
+    def __init__(self, count):
+        ptr = c_void_p()
+        check(lib().lbm_host_alloc(ctypes.byref(ptr), int(count) * 8), "lbm_host_alloc")
+        self.ptr = ptr.value
+        self.__array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (self.ptr, False), "version": 3}
+
+    def __del__(self):
+        ptr, self.ptr = getattr(self, "ptr", None), None
+        if ptr:
+            try:
+                lib().lbm_host_free(ptr)
+            except Exception:
+                pass
+
+
+PINNED_MIN_BYTES = 8 << 20
+
+
+def host_empty(shape):
+    """float64 host array for a device -> host copy: page-locked when it is large enough for the copy
+    speed to matter (PCIe DMA straight into the result, no driver staging), plain NumPy otherwise."""
+    import numpy as np
+
+    count = 1
+    for n in shape:
+        count *= int(n)
+    if count * 8 < PINNED_MIN_BYTES:
+        return np.empty(shape, dtype=np.float64)
+    try:
+        return np.asarray(_PinnedBlock(count)).reshape(shape)
+    except LbmError:
+        return np.empty(shape, dtype=np.float64)
+
+
 class KernelLibrary:
     """a generated per-scheme library (include/lbmk.h)."""
 

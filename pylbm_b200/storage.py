@@ -160,7 +160,7 @@ class DeviceArray(_ConsmMixin):
     def get(self, k0=0, nk=None):
         """dense host copy of populations k0..k0+nk-1: array [nk, *nspace]."""
         nk = self.nv - k0 if nk is None else nk
-        host = np.empty((nk,) + self.nspace, dtype=np.float64)
+        host = rt.host_empty((nk,) + self.nspace)
         rt.check(
             rt.lib().lbm_array_d2h(host.ctypes.data, self.ptr, ctypes.byref(self.grid), self.storage_id, k0, nk),
             "lbm_array_d2h",

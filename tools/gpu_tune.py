@@ -2,10 +2,11 @@
 import os, subprocess, sys
 root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 wl = sys.argv[1] if len(sys.argv) > 1 else "d3q19_lid_256"
+extra = os.environ.get("TUNE_ARGS", "").split()     # e.g. TUNE_ARGS="--dtype float32 --compute float32"
 for mb in (sys.argv[2:] or ["1", "4", "5", "6", "8"]):
     env = dict(os.environ, PYLBM_B200_MINBLOCKS=mb)
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", wl, "--steps", "30", "--warmup", "5",
-                          "--no-e2e", "--no-cpu-baseline"], env=env, capture_output=True, text=True)
+                          "--no-e2e", "--no-cpu-baseline"] + extra, env=env, capture_output=True, text=True)
     import json
     try:
         r = json.loads(out.stdout.strip().splitlines()[-1])
