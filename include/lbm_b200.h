@@ -124,6 +124,13 @@ int lbm_sim_add_bc(lbm_sim* sim, int kind, int64_t ncond, const int64_t* istore,
                    const double* dist, int nlevels, const int64_t* level_ptr,
                    const int* two_phase);
 int lbm_sim_set_rhs(lbm_sim* sim, int ibc, const double* rhs_host);
+/* Merged launches: the registered methods [group_ptr[g], group_ptr[g+1]) run as ONE kernel launch.
+ * The caller must have proved that, inside a group, no entry reads or overwrites a position that an
+ * entry of ANOTHER method of the group stores (results are then bit-identical to running the methods
+ * one after the other; fewer launches matter for small lattices).  A method in a group of more than
+ * one must be a single level without gather phase.  ngroups = 0 restores one launch sequence per
+ * method; registering another method does the same. */
+int lbm_sim_bc_groups(lbm_sim* sim, int ngroups, const int* group_ptr);
 int lbm_sim_set_scalars(lbm_sim* sim, const double* scalars, int nscalars);
 
 /* nsteps x (ghost update -> boundary methods -> fused pull stream+collide -> swap). */

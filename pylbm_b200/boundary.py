@@ -29,8 +29,37 @@ from .storage import HostArray
 
 __all__ = [
     "Boundary", "BoundaryMethod", "BounceBack", "BouzidiBounceBack", "AntiBounceBack",
-    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule",
+    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule", "merge_groups",
 ]
+
+
+def merge_groups(methods, max_group=12):
+    """
+    Greedy grouping of consecutive boundary methods into merged launches (lbm_sim_bc_groups).
+    `methods`: list of (store positions, [load position arrays], single_level) in application order.
+    A method joins the current group when it is a single gather-free level and no position it stores
+    is read or stored by the group, and no position it reads is stored by the group: the sequential
+    order of the methods is then irrelevant.  Returns group_ptr (len = ngroups + 1).
+    """
+    group_ptr = [0]
+    stores = loads = None
+    size = 0
+    for i, (st, lds, single) in enumerate(methods):
+        st = np.asarray(st, dtype=np.int64)
+        ld = np.concatenate([np.asarray(l, dtype=np.int64) for l in lds]) if lds else np.zeros(0, dtype=np.int64)
+        joinable = False
+        if i > 0 and single and prev_single and size < max_group:
+            joinable = not (np.isin(st, stores).any() or np.isin(st, loads).any() or np.isin(ld, stores).any())
+        if i > 0 and not joinable:
+            group_ptr.append(i)
+            stores = loads = None
+            size = 0
+        stores = st if stores is None else np.concatenate([stores, st])
+        loads = ld if loads is None else np.concatenate([loads, ld])
+        size += 1
+        prev_single = single if size == 1 else (prev_single and single)
+    group_ptr.append(len(methods))
+    return np.asarray(group_ptr, dtype=np.int32)
 
 
 def schedule(store, loads, snapshot=False):
@@ -52,7 +81,17 @@ def schedule(store, loads, snapshot=False):
     loads = [np.asarray(l, dtype=np.int64) for l in loads]
     level = np.zeros(n, dtype=np.int64)
     if n == 0:
-        return np.arange(0), np.array([0, 0], dtype=np.int64), np.array([1 if snapshot else 0], dtype=np.int32)
+        return np.arange(0), np.array([0, 0], dtype=np.int64), np.array([0], dtype=np.int32)
+
+    if snapshot:
+        # every read sees the state before the method started, so of several entries storing the same
+        # position only the LAST one matters (nobody reads the intermediate values): drop the others.
+        # One level; it gathers before it scatters only if some entry reads a position the method stores.
+        _, last = np.unique(store[::-1], return_index=True)
+        order = np.sort(n - 1 - last)
+        st = store[order]
+        alias = any(np.isin(l[order], st).any() for l in loads)
+        return order, np.array([0, order.size], dtype=np.int64), np.array([1 if alias else 0], dtype=np.int32)
 
     aliased = np.zeros(n, dtype=bool)          # entry reads something some entry stores
     for l in loads:
@@ -61,16 +100,14 @@ def schedule(store, loads, snapshot=False):
     dup_pos = uniq[counts > 1]
     duplicated = np.isin(store, dup_pos) if dup_pos.size else np.zeros(n, dtype=bool)
 
-    if not snapshot and (aliased.any() or duplicated.any()) or (snapshot and duplicated.any()):
+    if aliased.any() or duplicated.any():
         # positions involved in any hazard
         hazard_pos = set(dup_pos.tolist())
-        if not snapshot:
-            for l in loads:
-                hazard_pos.update(l[aliased].tolist())
+        for l in loads:
+            hazard_pos.update(l[aliased].tolist())
         involved = np.isin(store, np.fromiter(hazard_pos, dtype=np.int64, count=len(hazard_pos)))
         involved |= duplicated
-        if not snapshot:
-            involved |= aliased
+        involved |= aliased
         idx = np.nonzero(involved)[0]
         writers = collections.defaultdict(list)   # position -> earlier entries that store it
         readers = collections.defaultdict(list)   # position -> earlier entries that read it
@@ -79,17 +116,15 @@ def schedule(store, loads, snapshot=False):
             si = int(store[i])
             for j in writers.get(si, ()):                    # write-after-write
                 lev = max(lev, level[j] + 1)
-            if not snapshot:
-                for l in loads:                              # read-after-write
-                    for j in writers.get(int(l[i]), ()):
-                        lev = max(lev, level[j] + 1)
-                for j in readers.get(si, ()):                # write-after-read
-                    lev = max(lev, level[j])
+            for l in loads:                                  # read-after-write
+                for j in writers.get(int(l[i]), ()):
+                    lev = max(lev, level[j] + 1)
+            for j in readers.get(si, ()):                    # write-after-read
+                lev = max(lev, level[j])
             level[i] = lev
             writers[si].append(i)
-            if not snapshot:
-                for l in loads:
-                    readers[int(l[i])].append(i)
+            for l in loads:
+                readers[int(l[i])].append(i)
 
     order = np.argsort(level, kind="stable")
     nlev = int(level.max()) + 1
@@ -98,11 +133,8 @@ def schedule(store, loads, snapshot=False):
     two_phase = np.zeros(nlev, dtype=np.int32)
     for l in range(nlev):
         sel = order[level_ptr[l] : level_ptr[l + 1]]
-        if snapshot:
-            two_phase[l] = 1
-        else:
-            st = store[sel]
-            two_phase[l] = int(any(np.isin(ld[sel], st).any() for ld in loads))
+        st = store[sel]
+        two_phase[l] = int(any(np.isin(ld[sel], st).any() for ld in loads))
     return order, level_ptr, two_phase
 
 

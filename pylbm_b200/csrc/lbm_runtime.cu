@@ -354,6 +354,46 @@ static cudaError_t launch_bc(int kind, S* f, long long n, const long long* is, c
     return cudaErrorInvalidValue;
 }
 
+// All methods of a step in ONE launch, for the common case where the host has proved that no entry
+// of any method reads or overwrites what another entry stores (then the order of the methods and of
+// their entries is irrelevant).  Same arithmetic as k_bc (bit-identical results).
+#define LBM_BC_MAX_SEGMENTS 12
+struct BcSegment {
+    long long begin;   // first global entry index of this method
+    int kind;
+    const long long *istore, *iload0, *iload1;
+    const double *rhs, *dist;
+};
+struct BcSegments {
+    int n;
+    long long total;
+    BcSegment seg[LBM_BC_MAX_SEGMENTS];
+};
+
+template <typename S>
+__global__ void k_bc_multi(S* __restrict__ f, const BcSegments segs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= segs.total) return;
+    int m = segs.n - 1;
+    while (m > 0 && i < segs.seg[m].begin) --m;
+    const BcSegment& sg = segs.seg[m];
+    const long long j = i - sg.begin;
+    const double a = (double)f[sg.iload0[j]];
+    double v;
+    switch (sg.kind) {
+        case LBM_BC_BOUNCE_BACK: v = bc_value<LBM_BC_BOUNCE_BACK>(a, 0.0, sg.rhs[j], 0.0); break;
+        case LBM_BC_ANTI_BOUNCE_BACK: v = bc_value<LBM_BC_ANTI_BOUNCE_BACK>(a, 0.0, sg.rhs[j], 0.0); break;
+        case LBM_BC_BOUZIDI_BOUNCE_BACK:
+            v = bc_value<LBM_BC_BOUZIDI_BOUNCE_BACK>(a, (double)f[sg.iload1[j]], sg.rhs[j], sg.dist[j]);
+            break;
+        case LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK:
+            v = bc_value<LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK>(a, (double)f[sg.iload1[j]], sg.rhs[j], sg.dist[j]);
+            break;
+        default: v = a; break;   // Neumann
+    }
+    f[sg.istore[j]] = (S)v;
+}
+
 extern "C" int lbm_bc_apply(int kind, void* f, int storage, int64_t ncond, const int64_t* istore,
                             const int64_t* iload0, const int64_t* iload1, const double* rhs, const double* dist,
                             double* scratch, int two_phase, void* stream) {
@@ -471,6 +511,7 @@ struct lbm_sim {
     double t = 0.0;
     int64_t nt = 0;
     std::vector<BcMethod> bcs;
+    std::vector<int> bc_groups;                   // first method of each merged launch (+ end); empty: none
     double* scratch = nullptr;
     long long scratch_n = 0;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
@@ -635,8 +676,34 @@ extern "C" int lbm_sim_add_bc(lbm_sim* s, int kind, int64_t ncond, const int64_t
         s->scratch_n = maxlevel;
     }
     s->bcs.push_back(b);
+    s->bc_groups.clear();
     drop_graph(s);
     return (int)s->bcs.size() - 1;
+}
+
+extern "C" int lbm_sim_bc_groups(lbm_sim* s, int ngroups, const int* group_ptr) {
+    if (!s) return ARG_ERROR("null sim");
+    std::vector<int> groups;
+    if (ngroups > 0) {
+        if (!group_ptr) return ARG_ERROR("lbm_sim_bc_groups: null group_ptr");
+        groups.assign(group_ptr, group_ptr + ngroups + 1);
+        if (groups.front() != 0 || groups.back() != (int)s->bcs.size())
+            return ARG_ERROR("lbm_sim_bc_groups: group_ptr must span all registered methods");
+        for (int g = 0; g < ngroups; ++g) {
+            const int lo = groups[g], hi = groups[g + 1];
+            if (hi <= lo) return ARG_ERROR("lbm_sim_bc_groups: empty group");
+            if (hi - lo == 1) continue;
+            if (hi - lo > LBM_BC_MAX_SEGMENTS) return ARG_ERROR("lbm_sim_bc_groups: too many methods in a group");
+            for (int i = lo; i < hi; ++i) {
+                const BcMethod& b = s->bcs[i];
+                if (b.ncond > 0 && (b.level_ptr.size() != 2 || b.two_phase[0]))
+                    return ARG_ERROR("lbm_sim_bc_groups: a merged method must be one single-phase level");
+            }
+        }
+    }
+    s->bc_groups = groups;
+    drop_graph(s);
+    return 0;
 }
 
 extern "C" int lbm_sim_set_rhs(lbm_sim* s, int ibc, const double* rhs_host) {
@@ -692,21 +759,60 @@ static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
     return 0;
 }
 
+static int apply_bc_method(lbm_sim* s, BcMethod& b, void* f, cudaStream_t st) {
+    for (size_t l = 0; l + 1 < b.level_ptr.size(); ++l) {
+        const long long o = b.level_ptr[l], n = b.level_ptr[l + 1] - o;
+        if (n <= 0) continue;
+        cudaError_t e =
+            (s->d.storage == LBM_STORAGE_F64)
+                ? launch_bc<double>(b.kind, (double*)f, n, b.istore + o, b.iload0 + o,
+                                    b.iload1 ? b.iload1 + o : nullptr, b.rhs ? b.rhs + o : nullptr,
+                                    b.dist ? b.dist + o : nullptr, s->scratch, b.two_phase[l], st, &s->launches)
+                : launch_bc<float>(b.kind, (float*)f, n, b.istore + o, b.iload0 + o,
+                                   b.iload1 ? b.iload1 + o : nullptr, b.rhs ? b.rhs + o : nullptr,
+                                   b.dist ? b.dist + o : nullptr, s->scratch, b.two_phase[l], st, &s->launches);
+        if (e != cudaSuccess) return set_error(-(int)e, "boundary kernel", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
 static int apply_bcs(lbm_sim* s, void* f, cudaStream_t st) {
-    for (auto& b : s->bcs) {
-        for (size_t l = 0; l + 1 < b.level_ptr.size(); ++l) {
-            const long long o = b.level_ptr[l], n = b.level_ptr[l + 1] - o;
-            if (n <= 0) continue;
-            cudaError_t e =
-                (s->d.storage == LBM_STORAGE_F64)
-                    ? launch_bc<double>(b.kind, (double*)f, n, b.istore + o, b.iload0 + o,
-                                        b.iload1 ? b.iload1 + o : nullptr, b.rhs ? b.rhs + o : nullptr,
-                                        b.dist ? b.dist + o : nullptr, s->scratch, b.two_phase[l], st, &s->launches)
-                    : launch_bc<float>(b.kind, (float*)f, n, b.istore + o, b.iload0 + o,
-                                       b.iload1 ? b.iload1 + o : nullptr, b.rhs ? b.rhs + o : nullptr,
-                                       b.dist ? b.dist + o : nullptr, s->scratch, b.two_phase[l], st, &s->launches);
-            if (e != cudaSuccess) return set_error(-(int)e, "boundary kernel", cudaGetErrorString(e));
+    if (s->bc_groups.empty()) {
+        for (auto& b : s->bcs) {
+            int rc = apply_bc_method(s, b, f, st);
+            if (rc) return rc;
         }
+        return 0;
+    }
+    for (size_t g = 0; g + 1 < s->bc_groups.size(); ++g) {
+        const int lo = s->bc_groups[g], hi = s->bc_groups[g + 1];
+        if (hi - lo == 1) {
+            int rc = apply_bc_method(s, s->bcs[lo], f, st);
+            if (rc) return rc;
+            continue;
+        }
+        BcSegments segs;
+        segs.n = 0;
+        segs.total = 0;
+        for (int i = lo; i < hi; ++i) {
+            BcMethod& b = s->bcs[i];
+            if (b.ncond <= 0) continue;
+            BcSegment& sg = segs.seg[segs.n++];
+            sg.begin = segs.total;
+            sg.kind = b.kind;
+            sg.istore = b.istore; sg.iload0 = b.iload0; sg.iload1 = b.iload1;
+            sg.rhs = b.rhs; sg.dist = b.dist;
+            segs.total += b.ncond;
+        }
+        if (segs.total == 0) continue;
+        const unsigned blocks = (unsigned)((segs.total + 127) / 128);
+        if (s->d.storage == LBM_STORAGE_F64)
+            k_bc_multi<double><<<blocks, 128, 0, st>>>((double*)f, segs);
+        else
+            k_bc_multi<float><<<blocks, 128, 0, st>>>((float*)f, segs);
+        s->launches += 1;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return set_error(-(int)e, "boundary kernel", cudaGetErrorString(e));
     }
     return 0;
 }

@@ -97,6 +97,7 @@ _SIGNATURES = {
         [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     ),
     "lbm_sim_set_rhs": (c_int, [c_void_p, c_int, c_void_p]),
+    "lbm_sim_bc_groups": (c_int, [c_void_p, c_int, POINTER(c_int)]),
     "lbm_sim_set_scalars": (c_int, [c_void_p, POINTER(c_double), c_int]),
     "lbm_sim_step": (c_int, [c_void_p, c_int]),
     "lbm_sim_boundary_condition": (c_int, [c_void_p]),
@@ -153,29 +154,47 @@ def ensure_gpu():
 
 
 class _PinnedBlock:
-    """page-locked host memory exposed through the array interface; freed with the last view."""
+    """page-locked host memory exposed through the array interface.  Page-locking is slow (~0.5 s per
+    GB) while a DMA into page-locked memory is ~5x faster than a copy into pageable memory, so blocks
+    go back to a small pool when their last view dies and repeated reads of fields of the same size
+    (`sol.m[...]` every few steps) reuse them."""
+
+    _pool = {}          # nbytes -> [ptr, ...]
+    _pooled_bytes = 0
+    POOL_LIMIT = 16 << 30
 
     def __init__(self, count):
-        ptr = c_void_p()
-        check(lib().lbm_host_alloc(ctypes.byref(ptr), int(count) * 8), "lbm_host_alloc")
-        self.ptr = ptr.value
+        self.nbytes = int(count) * 8
+        free = _PinnedBlock._pool.get(self.nbytes)
+        if free:
+            self.ptr = free.pop()
+            _PinnedBlock._pooled_bytes -= self.nbytes
+        else:
+            ptr = c_void_p()
+            check(lib().lbm_host_alloc(ctypes.byref(ptr), self.nbytes), "lbm_host_alloc")
+            self.ptr = ptr.value
         self.__array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (self.ptr, False), "version": 3}
 
     def __del__(self):
         ptr, self.ptr = getattr(self, "ptr", None), None
-        if ptr:
-            try:
+        if not ptr:
+            return
+        try:
+            if _PinnedBlock._pooled_bytes + self.nbytes <= _PinnedBlock.POOL_LIMIT:
+                _PinnedBlock._pool.setdefault(self.nbytes, []).append(ptr)
+                _PinnedBlock._pooled_bytes += self.nbytes
+            else:
                 lib().lbm_host_free(ptr)
-            except Exception:
-                pass
+        except Exception:
+            pass
 
 
 PINNED_MIN_BYTES = 8 << 20
 
 
 def host_empty(shape):
-    """float64 host array for a device -> host copy: page-locked when it is large enough for the copy
-    speed to matter (PCIe DMA straight into the result, no driver staging), plain NumPy otherwise."""
+    """float64 host array for a device -> host copy: page-locked (pooled) when it is large enough
+    for the copy speed to matter, plain NumPy otherwise."""
     import numpy as np
 
     count = 1

@@ -285,6 +285,21 @@ class Simulation:
             method.fix_iload()
             method.set_rhs()
             method.move2gpu(self._handle, self.container.F)
+        if len(self.bc.methods) > 1:
+            # consecutive methods that provably do not interact run as one kernel launch
+            from .boundary import merge_groups
+
+            info = []
+            for method in self.bc.methods:
+                store, l0, l1, _, _, level_ptr, two_phase = method._keep
+                single = len(level_ptr) == 2 and not int(two_phase[0])
+                info.append((store, [l0] + ([l1] if l1 is not None else []), single))
+            groups = merge_groups(info)
+            if len(groups) - 1 < len(self.bc.methods):
+                rt.check(rt.lib().lbm_sim_bc_groups(self._handle, len(groups) - 1,
+                                                    groups.ctypes.data_as(ctypes.POINTER(ctypes.c_int))),
+                         "lbm_sim_bc_groups")
+            self.bc.groups = groups
         self._time_dependent = any(m.is_time_dependent for m in self.bc.methods)
         self._need_init = False
 

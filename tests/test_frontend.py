@@ -98,20 +98,56 @@ def test_schedule_levels_reproduce_sequential_semantics():
         src = f0.copy() if snapshot else f
         for i in range(n):
             f[store[i]] = 0.25 * src[l0[i]] + 0.5 * src[l1[i]] + i
-        # levelled execution
+        # levelled execution, modelled on the runtime (k_bc): a two-phase level gathers from the
+        # CURRENT array and then scatters; a one-phase level works in place, in any order
         order, ptr, two = schedule(store, [l0, l1], snapshot=snapshot)
         g = f0.copy()
-        idx = np.arange(n)[order]
         for lev in range(len(ptr) - 1):
-            sel = idx[ptr[lev]: ptr[lev + 1]]
-            base = f0 if snapshot else g
+            sel = order[ptr[lev]: ptr[lev + 1]]
             if two[lev]:
-                vals = 0.25 * base[l0[sel]] + 0.5 * base[l1[sel]] + sel
+                vals = 0.25 * g[l0[sel]] + 0.5 * g[l1[sel]] + sel
                 g[store[sel]] = vals
-            else:   # in place, any order inside the level must give the same result
+            else:
                 for i in sel[::-1]:
-                    g[store[i]] = 0.25 * base[l0[i]] + 0.5 * base[l1[i]] + i
+                    g[store[i]] = 0.25 * g[l0[i]] + 0.5 * g[l1[i]] + i
         assert np.array_equal(f, g), trial
+
+
+def test_merge_groups_keep_sequential_semantics():
+    """consecutive methods are merged into one launch only when the order of the methods cannot
+    matter; executing each group's entries in any order must reproduce the method-by-method loop."""
+    from pylbm_b200.boundary import merge_groups
+
+    rng = np.random.default_rng(1)
+    merged = 0
+    for trial in range(300):
+        npos = int(rng.integers(20, 80))
+        methods = []
+        for _ in range(int(rng.integers(1, 6))):
+            n = int(rng.integers(1, 6))
+            store = rng.choice(npos, size=n, replace=False)
+            load = rng.integers(0, npos, size=n)
+            single = not np.isin(load, store).any()
+            methods.append((store, [load], single))
+        ptr = merge_groups(methods)
+        assert ptr[0] == 0 and ptr[-1] == len(methods) and np.all(np.diff(ptr) > 0)
+        f0 = rng.uniform(size=npos)
+        f = f0.copy()
+        for store, (load,), _ in methods:          # method after method; a method reads a snapshot
+            f[store] = 2.0 * f[load] + 1.0          # (gather, then scatter)
+        g = f0.copy()
+        for a, b in zip(ptr[:-1], ptr[1:]):
+            if b - a == 1:
+                store, (load,), _ = methods[a]
+                g[store] = 2.0 * g[load] + 1.0
+                continue
+            merged += 1
+            entries = [(s_, l_) for store, (load,), single in methods[a:b] for s_, l_ in zip(store, load)]
+            assert all(single for _, _, single in methods[a:b])
+            for k in rng.permutation(len(entries)):    # one launch: entries in any order, in place
+                g[entries[k][0]] = 2.0 * g[entries[k][1]] + 1.0
+        assert np.array_equal(f, g), trial
+    assert merged > 20
 
 
 def test_boundary_lists_without_aliasing_are_single_level():
