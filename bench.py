@@ -338,8 +338,9 @@ def main():
     achieved = bytes_per_launch / (per_launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_peak()
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic_%s.json" % args.workload)
-    if os.path.exists(tpath) and args.dtype == "float64":
+    variant = "" if args.dtype == "float64" else ("_f32" if args.compute == "float32" else "_f32storage")
+    tpath = os.path.join(ROOT, "profiles", "traffic_%s%s.json" % (args.workload, variant))
+    if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:

@@ -345,7 +345,7 @@ static cudaError_t launch_bc(int kind, S* f, long long n, const long long* is, c
         case LBM_BC_ANTI_BOUNCE_BACK:
             return launch_bc_kind<S, LBM_BC_ANTI_BOUNCE_BACK>(f, n, is, l0, l1, rhs, dist, scratch, two_phase, st, nlaunch);
         case LBM_BC_BOUZIDI_BOUNCE_BACK:
-            return launch_bc_kind<S, LBM_BC_BOUZIDI_BOUNCE_BACK>(f, n, is, l0, l1, rhs, dist, scratch, 1, st, nlaunch);
+            return launch_bc_kind<S, LBM_BC_BOUZIDI_BOUNCE_BACK>(f, n, is, l0, l1, rhs, dist, scratch, two_phase, st, nlaunch);
         case LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK:
             return launch_bc_kind<S, LBM_BC_BOUZIDI_ANTI_BOUNCE_BACK>(f, n, is, l0, l1, rhs, dist, scratch, two_phase, st, nlaunch);
         case LBM_BC_NEUMANN:
@@ -398,7 +398,9 @@ extern "C" int lbm_bc_apply(int kind, void* f, int storage, int64_t ncond, const
                             const int64_t* iload0, const int64_t* iload1, const double* rhs, const double* dist,
                             double* scratch, int two_phase, void* stream) {
     if (!f || (ncond > 0 && (!istore || !iload0))) return ARG_ERROR("null pointer");
-    if ((two_phase || kind == LBM_BC_BOUZIDI_BOUNCE_BACK) && ncond > 0 && !scratch)
+    // stand-alone call: Bouzidi bounce-back always reads a snapshot (the reference's fcopy)
+    if (kind == LBM_BC_BOUZIDI_BOUNCE_BACK) two_phase = 1;
+    if (two_phase && ncond > 0 && !scratch)
         return ARG_ERROR("two-phase boundary kernel needs a scratch buffer");
     cudaError_t e =
         (storage == LBM_STORAGE_F64)
