@@ -559,7 +559,48 @@ def advection_d3q6(n=16, mod=None, perturb=None, generator="cuda"):
     }
 
 
+def advection_d2q13(nx=24, ny=20, mod=None, perturb=None, generator="cuda"):
+    """2-D advection-diffusion on D2Q13 (velocities up to +-2 on the axes: TWO ghost layers per side in
+    both directions), ragged sizes, periodic in y, prescribed value (bounce-back) on the left and
+    Neumann outflow on the right."""
+    mod = mod or _default_mod()
+    dx = 1.0 / ny
+    cx, cy = 0.3, -0.15
+    pol = [1, X, Y, X**2 + Y**2, X**2 - Y**2, X * Y, X**2 * Y, X * Y**2, X**3, Y**3,
+           X**2 * Y**2, X**4 + Y**4, X**4 - Y**4]
+    eq = [U, cx * U, cy * U, (cx**2 + cy**2 + 1.0) * U, (cx**2 - cy**2) * U, cx * cy * U,
+          cx * U / 2, cy * U / 2, cx * U, cy * U, U / 3, 2 * U, 0.0]
+    s = [0.0, 1.3, 1.3, 1.1, 1.5, 1.5, 1.2, 1.2, 1.4, 1.4, 1.0, 1.6, 1.6]
+
+    def blob(x, y):
+        return 1.0 + np.exp(-30 * ((x - 0.5) ** 2 + (y - 0.5) ** 2))
+
+    init = {U: blob}
+    if perturb is not None:
+        init = {U: _perturbed(perturb, 1.0, amp=0.2)}
+    return {
+        "box": {"x": [0.0, nx * dx], "y": [0.0, 1.0], "label": [0, 1, -1, -1]},
+        "space_step": dx,
+        "scheme_velocity": 1.0,
+        "schemes": [
+            {"velocities": list(range(13)), "conserved_moments": U, "polynomials": pol,
+             "equilibrium": eq, "relaxation_parameters": s}
+        ],
+        "init": init,
+        "boundary_conditions": {
+            0: {"method": {0: mod.bc.BounceBack}, "value": (_u_left_2d, (1.25,))},
+            1: {"method": {0: mod.bc.NeumannX}},
+        },
+        "generator": generator,
+    }
+
+
+def _u_left_2d(f, m, x, y, value):
+    m[U] = value
+
+
 CASES.update({
+    "advection_d2q13": advection_d2q13,
     "rayleigh_benard": rayleigh_benard,
     "advection_d1q5": advection_d1q5,
     "heat_d2q5": heat_d2q5,

@@ -35,4 +35,7 @@ PARITY_CASES = [
     ("advection_d1q5", dict(n=64)),                        # 1-D, ghost width 2, Neumann, bounce-back value
     ("heat_d2q5", dict(n=32)),                             # anti-BB, Bouzidi anti-BB, NeumannY, triangle, ellipse
     ("advection_d3q6", dict(n=12)),                        # 3-D periodic, init on distributions
+    # edge cases: ragged sizes (not multiples of the block / alignment), two ghost layers in 2-D
+    ("advection_d2q13", dict(nx=23, ny=19)),               # D2Q13: vmax = 2 on both axes, BB value + NeumannX
+    ("channel_sphere_d3q27", dict(nx=21, ny=13, nz=9)),    # 3-D, every extent odd
 ]
