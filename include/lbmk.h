@@ -90,6 +90,8 @@ int lbmk_one_time_step_peers(const void* fin, void* fout, const lbmk_grid* g, co
                              const lbmk_peers* peers, void* stream);
 int lbmk_transport(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_f2m(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+/* conserved moments only: fout has nconsm populations (rows 0..nconsm-1 of M f), same grid */
+int lbmk_f2m_consm(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_m2f(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_equilibrium(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_relaxation(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);

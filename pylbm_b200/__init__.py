@@ -16,8 +16,9 @@ from .domain import Domain, SlabTopology  # noqa: F401
 from .scheme import Scheme  # noqa: F401
 from . import boundary as bc  # noqa: F401
 from .simulation import Simulation  # noqa: F401
+from .hdf5 import H5File  # noqa: F401
 
 __all__ = [
     "Simulation", "Domain", "Scheme", "Stencil", "Velocity", "Geometry", "bc",
-    "Circle", "Ellipse", "Parallelogram", "Triangle", "Sphere", "Ellipsoid", "SlabTopology",
+    "Circle", "Ellipse", "Parallelogram", "Triangle", "Sphere", "Ellipsoid", "SlabTopology", "H5File",
 ]

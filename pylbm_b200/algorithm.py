@@ -236,6 +236,13 @@ class PullAlgorithm:
         out = self._linear(self.M, self.f)
         return self._ir("f2m", "f", self.f, self._zero_offsets(), "m", [], out, False)
 
+    def f2m_consm(self):
+        """conserved moments only (rows 0..nconsm-1 of M f): what `sol.m[symbol]` reads back after a
+        step, without materialising the other Q - nconsm rows (reference: simulation.py:215-224 runs the
+        full f2m over the whole array)."""
+        out = self._linear(self.M, self.f)[: self.nconsm]
+        return self._ir("f2m_consm", "f", self.f, self._zero_offsets(), "m", [], out, False)
+
     def m2f(self):
         out = self._linear(self.invM, self.m)
         return self._ir("m2f", "m", self.m, self._zero_offsets(), "f", [], out, False)
@@ -258,7 +265,8 @@ class PullAlgorithm:
         return self._ir("source_term", "m", self.m, self._zero_offsets(), "m", stm, list(self.m), True)
 
     def kernels(self):
-        out = [self.transport(), self.f2m(), self.m2f(), self.relaxation(), self.equilibrium(), self.one_time_step()]
+        out = [self.transport(), self.f2m(), self.f2m_consm(), self.m2f(), self.relaxation(), self.equilibrium(),
+               self.one_time_step()]
         if self.source_eq:
             out.append(self.source_term())
         return out

@@ -100,6 +100,13 @@ class CudaContainer:
             self._m = DeviceArray(self.nv, self._shape, self.vmax, "f64", self._consm, align=self.F.align)
         return self._m
 
+    @property
+    def mc(self):
+        """conserved moments only (nconsm rows, same element layout): target of `f2m_consm`."""
+        if getattr(self, "_mc", None) is None:
+            self._mc = DeviceArray(len(self._consm), self._shape, self.vmax, "f64", self._consm, align=self.F.align)
+        return self._mc
+
     def release_m(self):
         """free the moment array (it is rebuilt by f2m on the next `sol.m[...]`)."""
         self._m = None
@@ -153,11 +160,13 @@ class Simulation:
             from .stencil import Stencil
 
             topo = SlabTopology(Stencil.extract_dim(dico), rank, nranks)
+            topo.gather = gather          # used by H5File to bring the slabs to rank 0
         self.domain = Domain(dico, need_validation=False, topology=topo)
         self.scheme = Scheme(dico, check_inverse=check_inverse, need_validation=False)
         if self.domain.dim != self.scheme.dim:
             raise ValueError("Solution: the dimension of the domain and of the scheme are not the same")
 
+        self._mc_version = -1
         self._update_m = True
         self.t = 0.0
         self.nt = 0
@@ -200,6 +209,22 @@ class Simulation:
             self._initialize()
 
     # ------------------------------------------------------------------
+    # `_update_m = True` means "F changed, the moments are stale" (reference: simulation.py:215-224);
+    # every such assignment also invalidates the conserved-only copy
+    @property
+    def _update_m(self):
+        return self.__dict__.get("_update_m_flag", True)
+
+    @_update_m.setter
+    def _update_m(self, value):
+        self.__dict__["_update_m_flag"] = bool(value)
+        if value:
+            self.__dict__["_f_version"] = self.__dict__.get("_f_version", 0) + 1
+
+    @property
+    def _f_version(self):
+        return self.__dict__.get("_f_version", 0)
+
     @property
     def dt(self):
         if isinstance(self.dt_, sp.Expr):
@@ -403,6 +428,15 @@ class Simulation:
             self._update_m = False
             self.f2m()
 
+    def _conserved(self, key):
+        """interior values of one conserved moment, computed from F by the conserved-only kernel
+        (nconsm instead of Q rows of device memory and of store traffic)."""
+        c = self.container
+        if self._mc_version != self._f_version:
+            self._launch("f2m_consm", c.F, c.mc)
+            self._mc_version = self._f_version
+        return c.mc._in(key)
+
     @property
     def m_halo(self):
         def get(self_, i):
@@ -418,6 +452,13 @@ class Simulation:
     @property
     def m(self):
         def get(self_, i):
+            row = self_.container.F._key(i)
+            try:
+                row = int(row) if not isinstance(row, (slice, tuple, list, np.ndarray)) else -1
+            except (TypeError, ValueError):
+                row = -1
+            if self_._update_m and 0 <= row < len(self_.scheme.consm):
+                return self_._conserved(row)
             self_._refresh_m()
             return self_.container.m._in(i)
 

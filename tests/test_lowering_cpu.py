@@ -65,5 +65,5 @@ def test_generated_source_is_deterministic_and_describes_itself():
     a, ia = cudagen.generate_source(PullAlgorithm(scheme).kernels(), 3, 19)
     b, ib = cudagen.generate_source(PullAlgorithm(Scheme(cases.lid_cavity_d3q19(n=16))).kernels(), 3, 19)
     assert a == b and ia["hash"] == ib["hash"]
-    assert set(ia["routines"]) == {"transport", "f2m", "m2f", "relaxation", "equilibrium", "one_time_step"}
+    assert set(ia["routines"]) == {"transport", "f2m", "f2m_consm", "m2f", "relaxation", "equilibrium", "one_time_step"}
     assert "lbmk_kernel_one_time_step" in a and "__launch_bounds__" in a
