@@ -75,3 +75,94 @@ def test_slabs_reproduce_single_gpu(case, kw, halo):
         full = ref.m[key]
         assert whole.shape == full.shape
         assert np.abs(whole[fluid] - full[fluid]).max() <= 1e-12 * np.abs(full[fluid]).max()
+
+
+def _demo_worker(rank, world, nccl_id, test, nsteps, queue, halo, shared, barrier, h5dir):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import pylbm_b200
+    from pylbm_b200 import runtime as rt
+    from demo_fixtures import load_demo
+
+    rt.check(rt.lib().lbm_set_device(rank), "lbm_set_device")
+
+    def gather(blob):
+        shared[rank] = blob
+        barrier.wait()
+        out = [shared[r] for r in range(world)]
+        barrier.wait()
+        return out
+
+    dico, kwargs, record = load_demo(test)
+    sim = pylbm_b200.Simulation(dico, slab=(rank, world), nccl_id=nccl_id, gather=gather if halo == "peer" else None,
+                                **kwargs)
+    while sim.t < record["final_time"]:
+        sim.one_time_step()
+    assert sim.nt == nsteps
+    out = {str(k): sim.m[k].copy() for k in sim.scheme.consm}
+    if h5dir:
+        # the slabs are brought to rank 0 by the topology's all-gather (reference: hdf5.py:163-178)
+        h5 = pylbm_b200.H5File(sim.domain.mpi_topo, "slabs", h5dir)
+        h5.set_grid(*sim.domain.coords)
+        for k in sim.scheme.consm:
+            h5.add_scalar(str(k), sim.m[k])
+        h5.save()
+    sim.synchronize()
+    queue.put((rank, out))
+
+
+@pytest.mark.parametrize("test,halo", [
+    ("test2D_karman_vortex_street", "peer"), ("test2D_rayleigh_benard", "nccl"), ("test2D_orszag_Tang_vortex", "peer"),
+    ("test3D_karman", "peer"), ("test3D_poseuille", "nccl"), ("test1D_euler", "peer"),
+])
+def test_reference_demos_on_slabs(test, halo, tmp_path):
+    """dictionaries of the reference's demo tests, cut into x-slabs over the GPUs of the box, against the
+    fields of the unmodified reference (fluid cells: solid cells next to an interface may differ)."""
+    import ctypes
+    import multiprocessing as mp
+
+    import pylbm_b200
+    from pylbm_b200 import runtime as rt
+    from demo_fixtures import load_demo, load_results
+
+    ngpu = rt.lib().lbm_device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    expected = load_results(test)
+    raw = (ctypes.c_char * 128)()
+    rt.check(rt.lib().lbm_comm_unique_id(raw), "lbm_comm_unique_id")
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    manager = ctx.Manager()
+    shared, barrier = manager.dict(), manager.Barrier(world)
+    h5dir = str(tmp_path) if halo == "peer" else ""
+    procs = [ctx.Process(target=_demo_worker, args=(r, world, bytes(raw.raw), test, expected["nsteps"], queue, halo,
+                                                    shared, barrier, h5dir)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=900) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+
+    dico, _, _ = load_demo(test)
+    domain = pylbm_b200.Domain(dico)
+    fluid = domain.in_or_out[tuple(slice(v, -v) for v in list(domain.stencil.vmax)[: domain.dim])] == domain.valin
+    stride = expected["plane_stride"]
+    tol = 1e-12 * max(1.0, expected["nsteps"] / 100.0)
+    for key, want in expected["ref"].items():
+        whole = np.concatenate([results[r][key] for r in range(world)], axis=0)
+        mask = fluid
+        if stride > 1:
+            whole, mask = whole[::stride], fluid[::stride]
+        assert whole.shape == want.shape
+        err = np.abs(whole[mask] - want[mask]).max() / max(np.abs(want[mask]).max(), 1e-300)
+        assert err <= tol, (test, key, err)
+    if h5dir:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        from make_golden import H5Lite
+
+        back = H5Lite(os.path.join(h5dir, "slabs.h5")).datasets()
+        for key in expected["ref"]:
+            whole = np.concatenate([results[r][key] for r in range(world)], axis=0)
+            assert np.array_equal(back[key], whole.T)
