@@ -90,4 +90,5 @@ def test_save_like_the_3d_demos(tmp_path):
     sol._update_m = False
     full = sol.container.m._in(mass)
     sol._update_m = True
-    assert np.array_equal(full, sol.m[mass])
+    # (different common-subexpression grouping of the two kernels: last-bit differences only)
+    np.testing.assert_allclose(full, sol.m[mass], rtol=1e-14, atol=0)
