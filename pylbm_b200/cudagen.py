@@ -226,7 +226,13 @@ _KERNEL = r"""
 // byte offsets of the loads / stores relative to the cell, one per population: computed on the
 // host by the launcher and read from the kernel-parameter constant bank, so that an access costs
 // one 64-bit add (2 instructions) instead of re-deriving k*pstride + neighbour offset per thread
-struct lbmk_offs_%(name)s { long long in[%(nin)d]; long long out[%(nout)d]; };
+struct lbmk_offs_%(name)s {
+    long long in[%(nin)d];
+    long long out[%(nout)d];
+    unsigned fold;   // 0: blockIdx.y / blockIdx.z are the row group / the index of axis 0; otherwise the
+                     // number of row groups per axis-0 index, (z, y) being one linear index (more than
+                     // 65535 row groups or planes: e.g. a 2-D lattice with 100 000 rows)
+};
 
 __global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
 lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g,
@@ -240,9 +246,15 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
     const unsigned txshift = 31u - (unsigned)__clz(tx);
     const unsigned ty = LBMK_BLOCK >> txshift;
     const int i2 = g.lo[2] + (int)(blockIdx.x * tx + (tid & (tx - 1)));
-    const int i1 = g.lo[1] + (int)(blockIdx.y * ty + (tid >> txshift));
-    const int i0 = g.lo[0] + (int)blockIdx.z;
-    if (i2 >= g.hi[2] || i1 >= g.hi[1]) return;
+    unsigned by = blockIdx.y, bz = blockIdx.z;
+    if (offs.fold) {                       // uniform branch, not taken for ordinary shapes
+        const unsigned long long lin = (unsigned long long)blockIdx.z * gridDim.y + blockIdx.y;
+        bz = (unsigned)(lin / offs.fold);
+        by = (unsigned)(lin - (unsigned long long)bz * offs.fold);
+    }
+    const int i1 = g.lo[1] + (int)(by * ty + (tid >> txshift));
+    const int i0 = g.lo[0] + (int)bz;
+    if (i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]) return;
     const long long rowstride = g.pitch;
     const long long planestride = (long long)g.n[1] * g.pitch;
     const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
@@ -263,10 +275,19 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
     if (n0 <= 0 || n1 <= 0 || n2 <= 0) return 0;
     if (g->tx <= 0 || (g->tx & (g->tx - 1)) || g->tx > LBMK_BLOCK) return -3;
     const int ty = LBMK_BLOCK / g->tx;
-    const dim3 grid((unsigned)((n2 + g->tx - 1) / g->tx), (unsigned)((n1 + ty - 1) / ty), (unsigned)n0);
-    if (grid.y > 65535u || grid.z > 65535u) return -2;
+    dim3 grid((unsigned)((n2 + g->tx - 1) / g->tx), (unsigned)((n1 + ty - 1) / ty), (unsigned)n0);
     static const int noff[%(nin)d][3] = {%(offset_table)s};
     lbmk_offs_%(name)s offs;
+    offs.fold = 0;
+    if (grid.y > 65535u || grid.z > 65535u) {
+        // (row group, plane) as one linear index spread over (y, z)
+        const unsigned long long total = (unsigned long long)grid.y * grid.z;
+        offs.fold = grid.y;
+        grid.y = 32768u;
+        const unsigned long long gz = (total + grid.y - 1) / grid.y;
+        if (gz > 65535ull) return -2;
+        grid.z = (unsigned)gz;
+    }
     const long long plane = (long long)g->n[1] * g->pitch;
     for (int k = 0; k < %(nin)d; ++k)
         offs.in[k] = (k * g->pstride + noff[k][0] * plane + noff[k][1] * g->pitch + noff[k][2]) * (long long)sizeof(%(tin)s);
