@@ -124,6 +124,14 @@ int lbm_sim_add_bc(lbm_sim* sim, int kind, int64_t ncond, const int64_t* istore,
                    const double* dist, int nlevels, const int64_t* level_ptr,
                    const int* two_phase);
 int lbm_sim_set_rhs(lbm_sim* sim, int ibc, const double* rhs_host);
+/* flag != 0: method `ibc` is applied only when the ghost layers of the current array are NOT the ones
+ * the previous fused launch produced (first step, after lbm_sim_invalidate_ghosts).  Used for the
+ * entries of the walls handed to lbm_sim_set_walls: in steady state the fused kernel has already
+ * stored their values. */
+int lbm_sim_bc_stale_only(lbm_sim* sim, int ibc, int flag);
+/* Let the fused kernel apply the bounce-back walls of the fastest axis (lbmk_walls, lbmk.h);
+ * `launcher` = lbmk_one_time_step_walls of the kernel library.  walls = NULL switches it off. */
+int lbm_sim_set_walls(lbm_sim* sim, lbmk_launch_walls_fn launcher, const lbmk_walls* walls);
 /* Merged launches: the registered methods [group_ptr[g], group_ptr[g+1]) run as ONE kernel launch.
  * The caller must have proved that, inside a group, no entry reads or overwrites a position that an
  * entry of ANOTHER method of the group stores (results are then bit-identical to running the methods

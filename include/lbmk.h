@@ -64,6 +64,23 @@ typedef struct {
     int nin_lo;          /* interior size of the `lo` neighbour along the slab axis                    */
 } lbmk_peers;
 
+/*
+ * Bounce-back walls handled by the fused kernel itself.  When both faces normal to the FASTEST axis are
+ * plain bounce-back / anti-bounce-back walls (reference: boundary.py:400-469, 626-684), every cell next
+ * to such a wall stores, together with its new population moving towards the wall, the bounced value
+ * f_sym(k)(c + v_k) = +-f_k(c) + rhs[k] into the wall's ghost cell: the boundary entries of the NEXT
+ * step whose accesses are scattered 8-byte sectors in the list kernel (lbm_bc_apply), at the cost of
+ * the periodic-image stores they replace.  The caller (boundary.plan_walls) proves that the entries
+ * are complete, uniform per population and independent of every other entry.
+ */
+typedef struct {
+    int lo_plane;      /* index along the fastest axis of the cells next to the LOW wall  */
+    int hi_plane;      /* ... next to the HIGH wall                                       */
+    int neg_lo;        /* 0: bounce-back (+f), 1: anti-bounce-back (-f)                   */
+    int neg_hi;
+    double rhs[64];    /* per LOADED population k (the one moving towards the wall)       */
+} lbmk_walls;
+
 /* ABI version the library was generated for. */
 int lbmk_abi_version(void);
 
@@ -88,6 +105,11 @@ typedef int (*lbmk_launch_peers_fn)(const void* fin, void* fout, const lbmk_grid
                                     const lbmk_peers* peers, void* stream);
 int lbmk_one_time_step_peers(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
                              const lbmk_peers* peers, void* stream);
+/* same with walls of the fastest axis applied by the kernel (walls may be NULL) */
+typedef int (*lbmk_launch_walls_fn)(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                                    const lbmk_peers* peers, const lbmk_walls* walls, void* stream);
+int lbmk_one_time_step_walls(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                             const lbmk_peers* peers, const lbmk_walls* walls, void* stream);
 int lbmk_transport(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_f2m(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 /* conserved moments only: fout has nconsm populations (rows 0..nconsm-1 of M f), same grid */

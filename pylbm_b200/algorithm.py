@@ -225,7 +225,10 @@ class PullAlgorithm:
         tail, outputs = self._m2f_local()
         stm += tail
         offsets = [tuple(-int(c) for c in v) for v in self.velocities]
-        return self._ir("one_time_step", "f", f, offsets, "fnew", stm, outputs, True)
+        ir = self._ir("one_time_step", "f", f, offsets, "fnew", stm, outputs, True)
+        # population with the opposite velocity inside the same sub-scheme (bounce-back partner)
+        ir.symmetric = [int(k) for k in self.scheme.stencil.get_symmetric()]
+        return ir
 
     def transport(self):
         offsets = [tuple(-int(c) for c in v) for v in self.velocities]

@@ -29,7 +29,7 @@ from .storage import HostArray
 
 __all__ = [
     "Boundary", "BoundaryMethod", "BounceBack", "BouzidiBounceBack", "AntiBounceBack",
-    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule", "merge_groups",
+    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule", "merge_groups", "plan_walls",
 ]
 
 
@@ -60,6 +60,137 @@ def merge_groups(methods, max_group=12):
         prev_single = single if size == 1 else (prev_single and single)
     group_ptr.append(len(methods))
     return np.asarray(group_ptr, dtype=np.int32)
+
+
+def plan_walls(methods, array, velocities, symmetric):
+    """
+    Decide whether the bounce-back walls normal to the FASTEST axis can be applied by the fused kernel
+    itself (include/lbmk.h: lbmk_walls) and which list entries that replaces.
+
+    methods    [{"kind", "store", "loads": [positions, ...], "rhs", "eligible"}] in application order
+               (device positions of `array`, device order; `eligible` is False for methods whose
+               right-hand side changes in time or that are not a single gather-free level)
+    array      layout of the populations (storage.Layout / DeviceArray)
+    velocities integer lattice velocities [Q, dim];  symmetric: index of the opposite population
+
+    With walls on, every interior cell c of the two planes next to the faces stores, for every
+    population k moving towards the wall, `+-f_k(c) + rhs[k]` at W(c, k) = (sym k, c + v_k) right after
+    it has computed f_k(c), and the periodic images along the axis are no longer produced.  That equals
+    the reference (periodic update, then the methods in order, boundary.py / simulation.py:373-390) iff,
+    for each face:
+      * the entries `f[sym k](c + v_k) = +-f[k](c) + rhs` with c on the plane are all of one kind
+        (bounce-back or anti-bounce-back) and belong to eligible methods; the kernel uses the most
+        frequent right-hand side per population, and the entries that have it are REPLACED (removed
+        from the list);
+      * every other position W(c, k) the kernel writes (an entry with another right-hand side, e.g. an
+        edge cell labelled by the neighbouring face, or no bounce-back entry at all, e.g. next to an
+        outlet) is stored by a remaining list entry, which overwrites the kernel's value at the next
+        step, and is not read by any list entry;
+      * a replaced position is read only by entries of LATER methods (they saw the stored value in the
+        reference too), is stored by no other entry, and what a replaced entry reads is stored by nobody;
+      * no remaining entry reads a ghost cell of that side other than a replaced position.
+    Returns None, or (walls dict, [boolean mask of the replaced entries, one per method]).
+    """
+    dim = array.dim
+    n = array.canonical_n
+    w = array.canonical_vmax
+    if w[2] != 1 or n[2] < 4 or len(velocities) > 64:
+        return None
+    vel = np.zeros((len(velocities), 3), dtype=np.int64)
+    vel[:, 3 - dim:] = np.asarray(velocities, dtype=np.int64)[:, :dim]
+    if np.abs(vel[:, 2]).max() > 1:
+        return None
+    pstride, pitch, lead = array.pstride, array.pitch, array.lead
+
+    def decode(pos):
+        pos = np.asarray(pos, dtype=np.int64)
+        k = pos // pstride
+        r = pos - k * pstride - lead
+        row = r // pitch
+        return k, row // n[1], row % n[1], r - row * pitch
+
+    planes = {"lo": w[2], "hi": n[2] - w[2] - 1}
+    toward = {"lo": np.nonzero(vel[:, 2] < 0)[0], "hi": np.nonzero(vel[:, 2] > 0)[0]}
+    if toward["lo"].size == 0 or toward["hi"].size == 0:
+        return None
+    sym = np.asarray(symmetric, dtype=np.int64)
+    voff = (vel[:, 0] * n[1] + vel[:, 1]) * pitch + vel[:, 2]          # element offset of c + v_k
+    i0, i1 = np.meshgrid(np.arange(w[0], n[0] - w[0]), np.arange(w[1], n[1] - w[1]), indexing="ij")
+    rows = (i0 * n[1] + i1).ravel() * pitch + lead
+
+    masks = [np.zeros(len(m["store"]), dtype=bool) for m in methods]
+    walls = {"lo_plane": int(planes["lo"]), "hi_plane": int(planes["hi"]), "rhs": np.zeros(64)}
+    written = []
+    for side in ("lo", "hi"):
+        found_kind, per_method = None, []
+        for im, m in enumerate(methods):
+            if m["kind"] not in (rt.BC_BOUNCE_BACK, rt.BC_ANTI_BOUNCE_BACK) or len(m["store"]) == 0:
+                continue
+            store, load, rhs = np.asarray(m["store"]), np.asarray(m["loads"][0]), np.asarray(m["rhs"])
+            k, c0, c1, c2 = decode(load)
+            cand = (c2 == planes[side]) & np.isin(k, toward[side])
+            cand &= (c0 >= w[0]) & (c0 < n[0] - w[0]) & (c1 >= w[1]) & (c1 < n[1] - w[1])
+            if not cand.any():
+                continue
+            if not m["eligible"]:
+                return None
+            kc = k[cand]                     # the store must be the bounced population at c + v_k
+            if not np.array_equal(sym[kc] * pstride + (load[cand] - kc * pstride) + voff[kc], store[cand]):
+                return None
+            if found_kind is None:
+                found_kind = m["kind"]
+            elif found_kind != m["kind"]:
+                return None
+            per_method.append((im, cand, k, rhs))
+        if found_kind is None:
+            return None
+        walls["neg_" + side] = 1 if found_kind == rt.BC_ANTI_BOUNCE_BACK else 0
+        for kk in toward[side]:
+            vals = [rhs[cand & (k == kk)] for _, cand, k, rhs in per_method]
+            vals = np.concatenate(vals) if vals else np.zeros(0)
+            if vals.size == 0:
+                return None
+            uniq, cnt = np.unique(vals, return_counts=True)
+            walls["rhs"][int(kk)] = uniq[np.argmax(cnt)]
+            for im, cand, k, rhs in per_method:
+                masks[im] |= cand & (k == kk) & (rhs == walls["rhs"][int(kk)])
+            written.append(sym[kk] * pstride + rows + planes[side] + voff[kk])
+    written = np.concatenate(written)
+
+    empty = np.zeros(0, dtype=np.int64)
+    mine_store = np.concatenate([np.asarray(m["store"])[mask] for m, mask in zip(methods, masks)] + [empty])
+    mine_owner = np.concatenate([np.full(int(mask.sum()), im) for im, mask in enumerate(masks)] + [empty])
+    mine_load = np.concatenate([np.asarray(m["loads"][0])[mask] for m, mask in zip(methods, masks)] + [empty])
+    other_store = np.concatenate([np.asarray(m["store"])[~mask] for m, mask in zip(methods, masks)] + [empty])
+    if mine_store.size == 0 or np.unique(mine_store).size != mine_store.size:
+        return None
+    if np.isin(mine_store, other_store).any():
+        return None
+    if np.isin(mine_load, other_store).any() or np.isin(mine_load, mine_store).any():
+        return None
+    # what the kernel writes without a replaced entry behind it must be overwritten by the list
+    loose = written[~np.isin(written, mine_store)]
+    if not np.isin(loose, other_store).all():
+        return None
+    order = np.argsort(mine_store)
+    sorted_store, sorted_owner = mine_store[order], mine_owner[order]
+    for im, (m, mask) in enumerate(zip(methods, masks)):
+        for j, l in enumerate(m["loads"]):
+            l = np.asarray(l)
+            l = l[~mask] if j == 0 else l
+            if l.size == 0:
+                continue
+            if np.isin(l, loose).any():
+                return None
+            hit = np.isin(l, mine_store)
+            if hit.any():                      # only later methods may read a replaced position
+                owner = sorted_owner[np.searchsorted(sorted_store, l[hit])]
+                if (owner >= im).any():
+                    return None
+            _, _, _, c2 = decode(l[~hit])
+            if ((c2 < w[2]) | (c2 >= n[2] - w[2])).any():
+                return None
+    return walls, masks
 
 
 def schedule(store, loads, snapshot=False):
@@ -306,8 +437,8 @@ class BoundaryMethod:
         self._order = order
         return store[order], [l[order] for l in loads], level_ptr, two_phase
 
-    def move2gpu(self, sim_handle, array):
-        """register the method in the runtime (reference: boundary.py:378-397 move2gpu)."""
+    def prepare_device(self, array):
+        """device-order lists (positions in the padded layout, level schedule) kept in `_keep`."""
         store, loads, level_ptr, two_phase = self.device_lists(array)
         store = np.ascontiguousarray(store)
         l0 = np.ascontiguousarray(loads[0])
@@ -315,6 +446,26 @@ class BoundaryMethod:
         rhs = np.ascontiguousarray(self.rhs[self._order])
         dist = np.ascontiguousarray(self.s[self._order]) if hasattr(self, "s") else None
         self._keep = (store, l0, l1, rhs, dist, level_ptr, two_phase)
+        self._wall_mask = None
+        return self._keep
+
+    def move2gpu(self, sim_handle, array, wall_mask=None):
+        """register the method in the runtime (reference: boundary.py:378-397 move2gpu).  Entries
+        selected by `wall_mask` are applied by the fused kernel (plan_walls): they are left out of the
+        method's list and registered by the caller as a separate stale-only method."""
+        if getattr(self, "_keep", None) is None:
+            self.prepare_device(array)
+        store, l0, l1, rhs, dist, level_ptr, two_phase = self._keep
+        if wall_mask is not None and wall_mask.any():
+            keep = ~wall_mask                      # only single-level, gather-free methods get here
+            self._wall_mask = wall_mask
+            self._wall_lists = (np.ascontiguousarray(store[wall_mask]), np.ascontiguousarray(l0[wall_mask]),
+                                np.ascontiguousarray(rhs[wall_mask]))
+            self._order = self._order[keep]
+            store, l0, rhs = (np.ascontiguousarray(store[keep]), np.ascontiguousarray(l0[keep]),
+                              np.ascontiguousarray(rhs[keep]))
+            level_ptr = np.array([0, store.size], dtype=np.int64)
+            self._keep = (store, l0, l1, rhs, dist, level_ptr, two_phase)
         idx = rt.lib().lbm_sim_add_bc(
             sim_handle, self.kind, store.size, store.ctypes.data, l0.ctypes.data,
             l1.ctypes.data if l1 is not None else None, rhs.ctypes.data,

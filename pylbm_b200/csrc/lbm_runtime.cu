@@ -500,6 +500,7 @@ __global__ void k_wait(unsigned long long* flags) {
 // ---------------------------------------------------------------------------
 struct BcMethod {
     int kind = 0;
+    int stale_only = 0;      // skipped when the ghost layers come from the previous fused launch
     long long ncond = 0;
     long long *istore = nullptr, *iload0 = nullptr, *iload1 = nullptr;
     double *rhs = nullptr, *dist = nullptr;
@@ -514,6 +515,8 @@ struct lbm_sim {
     int64_t nt = 0;
     std::vector<BcMethod> bcs;
     std::vector<int> bc_groups;                   // first method of each merged launch (+ end); empty: none
+    lbmk_launch_walls_fn walls_fn = nullptr;      // fused kernel applies the walls of the fastest axis
+    lbmk_walls walls;
     double* scratch = nullptr;
     long long scratch_n = 0;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
@@ -683,6 +686,28 @@ extern "C" int lbm_sim_add_bc(lbm_sim* s, int kind, int64_t ncond, const int64_t
     return (int)s->bcs.size() - 1;
 }
 
+extern "C" int lbm_sim_bc_stale_only(lbm_sim* s, int ibc, int flag) {
+    if (!s || ibc < 0 || ibc >= (int)s->bcs.size()) return ARG_ERROR("lbm_sim_bc_stale_only: no such method");
+    s->bcs[ibc].stale_only = flag ? 1 : 0;
+    drop_graph(s);
+    return 0;
+}
+
+extern "C" int lbm_sim_set_walls(lbm_sim* s, lbmk_launch_walls_fn launcher, const lbmk_walls* walls) {
+    if (!s) return ARG_ERROR("null sim");
+    if (walls && !launcher) return ARG_ERROR("lbm_sim_set_walls: launcher missing");
+    if (walls) {
+        s->walls = *walls;
+        s->walls_fn = launcher;
+    } else {
+        s->walls_fn = nullptr;
+    }
+    // ghost values of the current array were produced under the previous setting
+    s->ghost_fresh = 0;
+    drop_graph(s);
+    return 0;
+}
+
 extern "C" int lbm_sim_bc_groups(lbm_sim* s, int ngroups, const int* group_ptr) {
     if (!s) return ARG_ERROR("null sim");
     std::vector<int> groups;
@@ -762,6 +787,7 @@ static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
 }
 
 static int apply_bc_method(lbm_sim* s, BcMethod& b, void* f, cudaStream_t st) {
+    if (b.stale_only && s->ghost_fresh) return 0;   // the previous fused launch stored these values
     for (size_t l = 0; l + 1 < b.level_ptr.size(); ++l) {
         const long long o = b.level_ptr[l], n = b.level_ptr[l + 1] - o;
         if (n <= 0) continue;
@@ -798,7 +824,7 @@ static int apply_bcs(lbm_sim* s, void* f, cudaStream_t st) {
         segs.total = 0;
         for (int i = lo; i < hi; ++i) {
             BcMethod& b = s->bcs[i];
-            if (b.ncond <= 0) continue;
+            if (b.ncond <= 0 || (b.stale_only && s->ghost_fresh)) continue;
             BcSegment& sg = segs.seg[segs.n++];
             sg.begin = segs.total;
             sg.kind = b.kind;
@@ -876,18 +902,21 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
     }
     lbmk_grid g = s->d.grid;
     g.wrap = s->wrap_mask;
+    lbmk_peers pr;
     if (s->peers_ready) {
         const int which = (fnew == s->buf[0]) ? 0 : 1;   // all ranks swap A/B in lockstep
-        lbmk_peers pr;
         pr.lo = s->peer_buf[0][which];
         pr.hi = s->peer_buf[1][which];
         pr.pstride_lo = s->peer_pstride[0];
         pr.pstride_hi = s->peer_pstride[1];
         pr.nin_lo = s->peer_nin_lo;
-        rc = s->d.one_time_step_peers(f, fnew, &g, scal, &pr, (void*)st);
-    } else {
-        rc = s->d.one_time_step(f, fnew, &g, scal, (void*)st);
     }
+    if (s->walls_fn)
+        rc = s->walls_fn(f, fnew, &g, scal, s->peers_ready ? &pr : nullptr, &s->walls, (void*)st);
+    else if (s->peers_ready)
+        rc = s->d.one_time_step_peers(f, fnew, &g, scal, &pr, (void*)st);
+    else
+        rc = s->d.one_time_step(f, fnew, &g, scal, (void*)st);
     if (rc) return set_error(rc, "one_time_step kernel launch", cudaGetErrorString((cudaError_t)(-rc)));
     if (ev1) cudaEventRecord(ev1, st);
     s->launches += 1;

@@ -212,6 +212,13 @@ typedef struct {       // per-axis description of the cells that own a periodic 
     long long dlow[3];
     long long dhigh[3];
 } lbmk_images;
+typedef struct {       // bounce-back walls normal to the fastest axis handled by the fused kernel itself
+    int lo_plane;      // index (fastest axis) of the cells next to the LOW wall
+    int hi_plane;      // ... next to the HIGH wall
+    int neg_lo;        // 0: bounce-back (+f), 1: anti bounce-back (-f)
+    int neg_hi;
+    double rhs[64];    // right-hand side per LOADED population (the one moving towards the wall)
+} lbmk_walls;
 #define SLAB %(slab)d
 
 typedef %(storage)s real_f;   // storage type of the populations in HBM
@@ -229,12 +236,13 @@ _KERNEL = r"""
 struct lbmk_offs_%(name)s {
     long long in[%(nin)d];
     long long out[%(nout)d];
+    long long wall[%(nout)d];   // fused kernel with walls: store position of the bounced population
     unsigned fold;   // 0: blockIdx.y / blockIdx.z are the row group / the index of axis 0; otherwise the
                      // number of row groups per axis-0 index, (z, y) being one linear index (more than
                      // 65535 row groups or planes: e.g. a 2-D lattice with 100 000 rows)
 };
 
-__global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
+%(template)s__global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
 lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g,
     const lbmk_offs_%(name)s offs%(peer_param)s%(scalar_params)s)
 {
@@ -293,8 +301,8 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
         offs.in[k] = (k * g->pstride + noff[k][0] * plane + noff[k][1] * g->pitch + noff[k][2]) * (long long)sizeof(%(tin)s);
     for (int k = 0; k < %(nout)d; ++k)
         offs.out[k] = k * g->pstride * (long long)sizeof(%(tout)s);
-%(images_launch)s    lbmk_kernel_%(name)s<<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
-        (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs%(peer_arg)s%(scalar_args)s);
+    for (int k = 0; k < %(nout)d; ++k) offs.wall[k] = 0;
+%(images_launch)s%(kernel_call)s
     return -(int)cudaGetLastError();
 }
 %(launch_tail)s"""
@@ -314,7 +322,10 @@ _IMAGES_PROLOGUE = r"""    // ---- periodic / neighbour images of this cell (see
     // the launcher (an inactive axis has thresholds that never match)
     const long long d0 = i0 < img.below[0] ? img.dlow[0] : (i0 >= img.above[0] ? img.dhigh[0] : 0LL);
     const long long d1 = i1 < img.below[1] ? img.dlow[1] : (i1 >= img.above[1] ? img.dhigh[1] : 0LL);
-    const long long d2 = i2 < img.below[2] ? img.dlow[2] : (i2 >= img.above[2] ? img.dhigh[2] : 0LL);
+    // (with walls on both faces of the fastest axis there is no periodic image along it)
+    const long long d2 = WALLZ ? 0LL : (i2 < img.below[2] ? img.dlow[2] : (i2 >= img.above[2] ? img.dhigh[2] : 0LL));
+    const bool wlo = WALLZ && i2 == walls.lo_plane, whi = WALLZ && i2 == walls.hi_plane;
+    (void)wlo; (void)whi;
     // array receiving the images that cross the SLAB axis (a neighbour's array with the peer halo)
     %(tout)s* qbase = fout;
     long long qps = g.pstride;
@@ -344,19 +355,32 @@ _IMAGES_LAUNCH = r"""
             img.dlow[a] = on ? (long long)(peer_ ? pp->nin_lo : nin) * stride_[a] : 0;
             img.dhigh[a] = on ? -(long long)nin * stride_[a] : 0;
         }
+        // bounced population sym(k) at the neighbour c + v_k = c - noff[k] (only used with walls)
+        static const int sym_[%(nout)d] = {%(sym_table)s};
+        for (int k = 0; k < %(nout)d; ++k)
+            offs.wall[k] = (sym_[k] * g->pstride - (noff[k][0] * stride_[0] + noff[k][1] * stride_[1] + noff[k][2]))
+                           * (long long)sizeof(%(tout)s);
     }
 """
 
 
-def _inline_image(v, k, slab):
+def _inline_image(v, k, slab, tout):
     """store suffix for the image that only crosses the FASTEST axis (two lanes of every row): done
-    with the main store from the register value -- no re-read, no divergent tail."""
+    with the main store from the register value -- no re-read, no divergent tail.  In the WALLZ
+    instantiation the same lanes store the bounced value into the wall's ghost cell instead
+    (bounce_back / anti_bounce_back of the NEXT step, reference boundary.py:462-464, 678-680, with the
+    arithmetic of the list kernel k_bc: explicit round-to-nearest add, no contraction)."""
     if v[2] == 0:
         return ""
     cond = "p2" if v[2] > 0 else "m2"
     if slab == 2:
-        return " if (%s) qbase[%dLL * qps + cell + d2] = o_;" % (cond, k)
-    return " if (%s) __stcg(p_ + d2, o_);" % cond
+        image = " if (%s) qbase[%dLL * qps + cell + d2] = o_;" % (cond, k)
+    else:
+        image = " if (%s) __stcg(p_ + d2, o_);" % cond
+    wall, neg = ("wlo", "walls.neg_lo") if v[2] < 0 else ("whi", "walls.neg_hi")
+    bounce = (" if (%s) __stcg((%s*)(pout + offs.wall[%d]), (%s)__dadd_rn(%s ? -(double)o_ : (double)o_, walls.rhs[%d]));"
+              % (wall, tout, k, tout, neg, k))
+    return " if (!WALLZ) {%s } else {%s }" % (image, bounce)
 
 
 def _images_code(velocities, tout, slab):
@@ -395,14 +419,28 @@ def _canonical(offset):
 
 
 _LAUNCH_HEAD = 'extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)'
-_LAUNCH_HEAD_PEERS = ('extern "C" int lbmk_%(name)s_peers(const void* fin, void* fout, const lbmk_grid* g, '
-                      'const double* scalars, const lbmk_peers* peers, void* stream)')
-_LAUNCH_TAIL_PEERS = """
+_LAUNCH_HEAD_WALLS = ('extern "C" int lbmk_%(name)s_walls(const void* fin, void* fout, const lbmk_grid* g, '
+                      'const double* scalars, const lbmk_peers* peers, const lbmk_walls* walls, void* stream)')
+_LAUNCH_TAIL_WALLS = """
+extern "C" int lbmk_%(name)s_peers(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                                   const lbmk_peers* peers, void* stream)
+{
+    return lbmk_%(name)s_walls(fin, fout, g, scalars, peers, nullptr, stream);
+}
 extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)
 {
-    return lbmk_%(name)s_peers(fin, fout, g, scalars, nullptr, stream);
+    return lbmk_%(name)s_walls(fin, fout, g, scalars, nullptr, nullptr, stream);
 }
 """
+_CALL_PLAIN = """    lbmk_kernel_%(name)s<<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
+        (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs%(scalar_args)s);"""
+_CALL_WALLS = """    const lbmk_peers pr_ = peers ? *peers : lbmk_peers{nullptr, nullptr, 0, 0, 0};
+    if (walls)
+        lbmk_kernel_%(name)s<true><<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
+            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, *walls%(scalar_args)s);
+    else
+        lbmk_kernel_%(name)s<false><<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
+            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, lbmk_walls{}%(scalar_args)s);"""
 
 
 def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0, compute="double"):
@@ -421,7 +459,7 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         vels = [tuple(-o for o in _canonical(off)) for off in ir.in_offsets]
         stores = [
             "    { const %s o_ = (%s)(%s); %s* p_ = (%s*)(pout + offs.out[%d]); __stcg(p_, o_);%s }"
-            % (tout, tout, pr.doprint(o), tout, tout, k, _inline_image(vels[k], k, slab))
+            % (tout, tout, pr.doprint(o), tout, tout, k, _inline_image(vels[k], k, slab, tout))
             for k, o in enumerate(outs)
         ]
     else:
@@ -433,6 +471,8 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
     scal_params = "".join(", const real_c_%s %s" % (ir.name, _c_name(s)) for s in ir.scalars)
     scal_args = "".join(", (real_c_%s)scalars[%d]" % (ir.name, i) for i in range(len(ir.scalars)))
     table = ", ".join("{%d, %d, %d}" % _canonical(off) for off in ir.in_offsets)
+    symmetric = getattr(ir, "symmetric", None) or list(range(len(outs)))
+    sym_table = ", ".join(str(int(k)) for k in symmetric)
     src = "typedef %s real_c_%s;\n" % (compute, ir.name) + _KERNEL % dict(
         name=ir.name,
         tin=tin,
@@ -448,11 +488,12 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         loads="\n".join(loads),
         images=_images_code([tuple(-o for o in _canonical(off)) for off in ir.in_offsets], tout, slab) if images else "",
         prologue=(_IMAGES_PROLOGUE % dict(tout=tout)) if images else "",
-        peer_param=", const lbmk_peers pr, const lbmk_images img" if images else "",
-        peer_arg=", (peers ? *peers : lbmk_peers{nullptr, nullptr, 0, 0, 0}), img" if images else "",
-        images_launch=_IMAGES_LAUNCH if images else "",
-        launch_head=(_LAUNCH_HEAD_PEERS if images else _LAUNCH_HEAD) % dict(name=ir.name),
-        launch_tail=(_LAUNCH_TAIL_PEERS % dict(name=ir.name)) if images else "",
+        template="template <bool WALLZ>\n" if images else "",
+        peer_param=", const lbmk_peers pr, const lbmk_images img, const lbmk_walls walls" if images else "",
+        images_launch=(_IMAGES_LAUNCH % dict(nout=len(outs), tout=tout, sym_table=sym_table)) if images else "",
+        kernel_call=(_CALL_WALLS if images else _CALL_PLAIN) % dict(name=ir.name, tin=tin, tout=tout, scalar_args=scal_args),
+        launch_head=(_LAUNCH_HEAD_WALLS if images else _LAUNCH_HEAD) % dict(name=ir.name),
+        launch_tail=(_LAUNCH_TAIL_WALLS % dict(name=ir.name)) if images else "",
         body="\n".join(body),
         stores="\n".join(stores),
     )

@@ -14,7 +14,7 @@ from ctypes import (
 
 from . import build
 
-__all__ = ["LbmkGrid", "LbmSimDesc", "lib", "check", "LbmError", "KernelLibrary", "ensure_gpu"]
+__all__ = ["LbmkGrid", "LbmkWalls", "LbmSimDesc", "lib", "check", "LbmError", "KernelLibrary", "ensure_gpu"]
 
 STORAGE_F64, STORAGE_F32 = 0, 1
 BC_BOUNCE_BACK, BC_ANTI_BOUNCE_BACK, BC_BOUZIDI_BOUNCE_BACK, BC_BOUZIDI_ANTI_BOUNCE_BACK, BC_NEUMANN = range(5)
@@ -41,6 +41,12 @@ class LbmkGrid(Structure):
         out = LbmkGrid()
         ctypes.memmove(ctypes.byref(out), ctypes.byref(self), ctypes.sizeof(LbmkGrid))
         return out
+
+
+class LbmkWalls(Structure):
+    """include/lbmk.h: lbmk_walls"""
+    _fields_ = [("lo_plane", c_int), ("hi_plane", c_int), ("neg_lo", c_int), ("neg_hi", c_int),
+                ("rhs", c_double * 64)]
 
 
 LAUNCH_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, POINTER(LbmkGrid), POINTER(c_double), c_void_p)
@@ -98,6 +104,8 @@ _SIGNATURES = {
     ),
     "lbm_sim_set_rhs": (c_int, [c_void_p, c_int, c_void_p]),
     "lbm_sim_bc_groups": (c_int, [c_void_p, c_int, POINTER(c_int)]),
+    "lbm_sim_bc_stale_only": (c_int, [c_void_p, c_int, c_int]),
+    "lbm_sim_set_walls": (c_int, [c_void_p, c_void_p, c_void_p]),
     "lbm_sim_set_scalars": (c_int, [c_void_p, POINTER(c_double), c_int]),
     "lbm_sim_step": (c_int, [c_void_p, c_int]),
     "lbm_sim_boundary_condition": (c_int, [c_void_p]),

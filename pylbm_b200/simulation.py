@@ -305,28 +305,74 @@ class Simulation:
         """(reference: simulation.py:155-163)"""
         self._create_handle()
         self.initialization()
+        F = self.container.F
         for method in self.bc.methods:
             method.prepare_rhs(self)
             method.fix_iload()
             method.set_rhs()
-            method.move2gpu(self._handle, self.container.F)
-        if len(self.bc.methods) > 1:
+            method.prepare_device(F)
+        masks = self._plan_walls()
+        # device methods in application order; the entries a wall plan takes out of a method follow it
+        # immediately as a stale-only method (same place in the sequence as in the reference)
+        info = []
+        self._wall_keep = []
+        lib = rt.lib()
+        for method, mask in zip(self.bc.methods, masks):
+            method.move2gpu(self._handle, F, wall_mask=mask)
+            store, l0, l1, _, _, level_ptr, two_phase = method._keep
+            single = len(level_ptr) == 2 and not int(two_phase[0])
+            info.append((store, [l0] + ([l1] if l1 is not None else []), single))
+            if mask is not None and mask.any():
+                wstore, wl0, wrhs = method._wall_lists
+                idx = lib.lbm_sim_add_bc(self._handle, method.kind, wstore.size, wstore.ctypes.data, wl0.ctypes.data,
+                                         None, wrhs.ctypes.data, None, 0, None, None)
+                rt.check(idx, "lbm_sim_add_bc(wall entries)")
+                rt.check(lib.lbm_sim_bc_stale_only(self._handle, idx, 1), "lbm_sim_bc_stale_only")
+                self._wall_keep.append((wstore, wl0, wrhs))
+                info.append((wstore, [wl0], False))          # never merged with its neighbours
+        if self.bc.walls is not None:
+            w = rt.LbmkWalls()
+            w.lo_plane, w.hi_plane = self.bc.walls["lo_plane"], self.bc.walls["hi_plane"]
+            w.neg_lo, w.neg_hi = self.bc.walls["neg_lo"], self.bc.walls["neg_hi"]
+            for k in range(64):
+                w.rhs[k] = float(self.bc.walls["rhs"][k])
+            rt.check(lib.lbm_sim_set_walls(self._handle, self.kernels.address("one_time_step_walls"), ctypes.byref(w)),
+                     "lbm_sim_set_walls")
+        if len(info) > 1:
             # consecutive methods that provably do not interact run as one kernel launch
             from .boundary import merge_groups
 
-            info = []
-            for method in self.bc.methods:
-                store, l0, l1, _, _, level_ptr, two_phase = method._keep
-                single = len(level_ptr) == 2 and not int(two_phase[0])
-                info.append((store, [l0] + ([l1] if l1 is not None else []), single))
             groups = merge_groups(info)
-            if len(groups) - 1 < len(self.bc.methods):
-                rt.check(rt.lib().lbm_sim_bc_groups(self._handle, len(groups) - 1,
-                                                    groups.ctypes.data_as(ctypes.POINTER(ctypes.c_int))),
+            if len(groups) - 1 < len(info):
+                rt.check(lib.lbm_sim_bc_groups(self._handle, len(groups) - 1,
+                                               groups.ctypes.data_as(ctypes.POINTER(ctypes.c_int))),
                          "lbm_sim_bc_groups")
             self.bc.groups = groups
         self._time_dependent = any(m.is_time_dependent for m in self.bc.methods)
         self._need_init = False
+
+    def _plan_walls(self):
+        """bounce-back walls of the fastest axis applied by the fused kernel (boundary.plan_walls)."""
+        from .boundary import plan_walls
+
+        self.bc.walls = None
+        none = [None] * len(self.bc.methods)
+        if os.environ.get("PYLBM_B200_NO_WALLS") or not self.bc.methods:
+            return none
+        if self.nranks > 1 and self.dim == 1:
+            return none                     # the fastest axis is the slab axis
+        info = []
+        for method in self.bc.methods:
+            store, l0, l1, rhs, _, level_ptr, two_phase = method._keep
+            eligible = len(level_ptr) == 2 and not int(two_phase[0]) and not method.is_time_dependent
+            info.append({"kind": method.kind, "store": store, "loads": [l0] + ([l1] if l1 is not None else []),
+                         "rhs": rhs, "eligible": eligible})
+        plan = plan_walls(info, self.container.F, self.scheme.stencil.get_all_velocities(),
+                          self.scheme.stencil.get_symmetric())
+        if plan is None:
+            return none
+        self.bc.walls, masks = plan
+        return masks
 
     def initialization(self):
         """(reference: simulation.py:258-320)"""

@@ -66,6 +66,32 @@ class HostArray(_ConsmMixin):
         self.array[self._key(key)] = values
 
 
+class Layout:
+    """element layout of a padded SoA array (no device memory: usable on the build box)."""
+
+    def __init__(self, nv, nspace, vmax, itemsize=8, align=None):
+        self.nv = int(nv)
+        self.nspace = tuple(int(n) for n in nspace)
+        self.dim = len(self.nspace)
+        self.vmax = [int(v) for v in vmax]
+        n = (1,) * (3 - self.dim) + self.nspace
+        w = (0,) * (3 - self.dim) + tuple(self.vmax)
+        align = int(align) if align else 128 // itemsize
+        self.align = align
+        self.pitch = _roundup(n[2], align)
+        self.lead = (align - w[2]) % align
+        self.pstride = _roundup(self.lead + n[0] * n[1] * self.pitch, align)
+        self.canonical_n, self.canonical_vmax = n, w
+
+    def positions(self, index):
+        """element positions of entries [k, ix(, iy(, iz))] given as an integer array (dim+1, n)."""
+        index = np.asarray(index, dtype=np.int64)
+        k = index[0]
+        space = [np.zeros_like(k)] * (3 - self.dim) + [index[1 + d] for d in range(self.dim)]
+        n = self.canonical_n
+        return k * self.pstride + self.lead + (space[0] * n[1] + space[1]) * self.pitch + space[2]
+
+
 class DeviceArray(_ConsmMixin):
     """
     Padded SoA array in HBM.  `nspace` includes the ghost layers (`vmax` per side).
