@@ -256,3 +256,49 @@ def test_runtime_scalars_from_extra_parameters():
     b.one_time_step()
     for key in a.scheme.consm:
         assert np.abs(a.m[key] - b.m[key]).max() <= 1e-14
+
+
+@pytest.mark.parametrize("name,kw,dtype", [
+    ("lid_cavity_d3q19", dict(n=16), "float64"), ("channel_sphere_d3q27", dict(nx=21, ny=13, nz=9), "float64"),
+    ("lid_cavity_d3q19", dict(n=12), "float32"),
+])
+def test_walls_in_the_fused_kernel_are_bit_identical_to_the_list_kernel(name, kw, dtype, monkeypatch):
+    """bounce-back walls normal to the fastest axis are applied by the fused kernel (lbmk_walls) when
+    boundary.plan_walls proves it equivalent; the arithmetic is the list kernel's, so the populations
+    must be IDENTICAL to a run with the plan switched off -- including after an outside write of F,
+    which sends one step through the stale-only fallback entries."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    def run(walls):
+        if walls:
+            monkeypatch.delenv("PYLBM_B200_NO_WALLS", raising=False)
+        else:
+            monkeypatch.setenv("PYLBM_B200_NO_WALLS", "1")
+        sim = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw), dtype=dtype)
+        assert (sim.bc.walls is not None) == walls
+        sim.run(9)
+        sim.one_time_step()
+        sim.boundary_condition()
+        sim.F_halo[1] = sim.F_halo[1]          # outside write: ghosts stale, next step uses the full lists
+        sim.run(6)
+        sim.one_time_step()
+        return sim
+
+    a, b = run(True), run(False)
+    replaced = sum(int(m._wall_mask.sum()) for m in a.bc.methods if getattr(m, "_wall_mask", None) is not None)
+    assert replaced > 0
+    inner = (slice(None),) + tuple(slice(v, -v) for v in a.domain.stencil.vmax)
+    assert np.array_equal(a.container.F.get()[inner], b.container.F.get()[inner])
+    for key in a.scheme.consm:
+        assert np.array_equal(a.m[key], b.m[key])
+
+
+def test_wall_plan_is_refused_when_it_would_change_results():
+    """Bouzidi walls, Neumann faces or periodic boxes never get the fused-kernel walls."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    for name, kw in [("karman_d2q9", dict(nx=64, ny=32)), ("shallow_water_d2q4", dict(n=32)), ("heat_d2q5", dict(n=32))]:
+        sim = pylbm_b200.Simulation(cases.CASES[name](**kw))
+        assert sim.bc.walls is None, name
