@@ -166,3 +166,49 @@ def test_boundary_lists_without_aliasing_are_single_level():
     order, ptr, two = schedule(pos(method.istore), [pos(method.iload[0])])
     assert len(ptr) == 2 and not two[0] and np.array_equal(order, np.arange(order.size))
     assert method.istore.shape == (6 * 12 * 12 * 5 - 0, 4) or method.istore.shape[1] == 4
+
+
+def test_plan_walls_on_the_parity_workloads():
+    """host proof for the fused-kernel walls (boundary.plan_walls) on real boundary lists: the D3Q19
+    cavity and the D3Q27 channel qualify (entries with another right-hand side or owned by the outlet
+    stay in the list), Bouzidi / Neumann / periodic cases do not."""
+    import pylbm_b200 as lb
+    from pylbm_b200 import cases
+    from pylbm_b200.boundary import Boundary, plan_walls, schedule
+    from pylbm_b200.scheme import Scheme
+    from pylbm_b200.storage import Layout
+
+    def plan(dico):
+        dom, sch = lb.Domain(dico), Scheme(dico)
+        bc = Boundary(dom, None, dico)
+        nv = int(sch.stencil.nv_ptr[-1])
+        lay = Layout(nv, dom.shape_halo, list(dom.stencil.vmax))
+        methods = []
+        for m in bc.methods:
+            m.set_iload()
+            m.fix_iload()
+            store = lay.positions(m.istore.T)
+            loads = [lay.positions(l.T) for l in m.iload]
+            order, ptr, two = schedule(store, loads, snapshot=m.snapshot)
+            rhs = 0.25 * np.asarray(m.ilabel, dtype=float)[order]     # label-dependent stand-in
+            methods.append({"kind": m.kind, "store": store[order], "loads": [l[order] for l in loads],
+                            "rhs": rhs, "eligible": len(ptr) == 2 and not two[0]})
+        return plan_walls(methods, lay, sch.stencil.get_all_velocities(), sch.stencil.get_symmetric()), methods
+
+    res, methods = plan(cases.lid_cavity_d3q19(n=12))
+    walls, masks = res
+    # two faces x 12^2 cells x 5 populations, minus the edge entries labelled by the side walls
+    assert 2 * 144 * 5 - 2 * 48 <= int(masks[0].sum()) < 2 * 144 * 5
+    assert walls["lo_plane"] == 1 and walls["hi_plane"] == 12 and walls["neg_lo"] == walls["neg_hi"] == 0
+    assert walls["rhs"][:19].max() == 0.25 and walls["rhs"][:19].min() == 0.0
+    res, methods = plan(cases.channel_sphere_d3q27(nx=16, ny=8, nz=8))
+    assert res is not None and int(res[1][0].sum()) > 0 and not res[1][1].any() and not res[1][2].any()
+    for dico in (cases.karman_d2q9(nx=64, ny=32), cases.heat_d2q5(n=24), cases.advection_d2q13(nx=23, ny=19)):
+        assert plan(dico)[0] is None
+    # a time-dependent (not eligible) owner refuses the plan
+    res, methods = plan(cases.lid_cavity_d3q19(n=12))
+    for m in methods:
+        m["eligible"] = False
+    lay = Layout(19, [14, 14, 14], [1, 1, 1])
+    sch = Scheme(cases.lid_cavity_d3q19(n=12))
+    assert plan_walls(methods, lay, sch.stencil.get_all_velocities(), sch.stencil.get_symmetric()) is None
