@@ -359,8 +359,12 @@ class Simulation:
         none = [None] * len(self.bc.methods)
         if os.environ.get("PYLBM_B200_NO_WALLS") or not self.bc.methods:
             return none
-        if self.nranks > 1 and self.dim == 1:
-            return none                     # the fastest axis is the slab axis
+        if self.nranks > 1 and (self.dim == 1 or self._gather is None):
+            # 1-D: the fastest axis is the slab axis.  NCCL halo: whole slab-face planes are copied
+            # at the start of a step, ghost rows of the fastest axis included, which would overwrite the
+            # corner values the kernel stored at the end of the previous step (the peer halo only
+            # stores the populations that cross the slab face)
+            return none
         info = []
         for method in self.bc.methods:
             store, l0, l1, rhs, _, level_ptr, two_phase = method._keep
