@@ -490,14 +490,37 @@ def _t_wall(f, m, x, y, value):
     m[T] = value
 
 
-def heat_d2q5(n=48, mod=None, perturb=None, generator="cuda"):
+def heat_d2q5(n=48, mod=None, perturb=None, generator="cuda", plain=False):
     """2-D heat equation, D2Q5 with anti bounce-back (Dirichlet) walls, a solid triangle and an
-    elliptic hole treated with Bouzidi anti bounce-back, Neumann in y on the top wall."""
+    elliptic hole treated with Bouzidi anti bounce-back, Neumann in y on the top wall.
+    plain=True: periodic in x, anti bounce-back (two different temperatures) on both y walls, no
+    obstacle -- the 2-D case whose walls the fused kernel can apply itself (lbmk_walls)."""
     mod = mod or _default_mod()
     dx = 1.0 / n
     init = {T: 0.0}
     if perturb is not None:
         init = {T: _perturbed(perturb, 0.5, amp=0.3)}
+    if plain:
+        return {
+            "box": {"x": [0.0, 1.0], "y": [0.0, 1.0], "label": [-1, -1, 0, 1]},
+            "space_step": dx,
+            "scheme_velocity": 1.0,
+            "schemes": [
+                {
+                    "velocities": list(range(5)),
+                    "conserved_moments": T,
+                    "polynomials": [1, X, Y, (X**2 + Y**2) / 2, (X**2 - Y**2) / 2],
+                    "equilibrium": [T, 0.0, 0.0, 0.4 * T, 0.0],
+                    "relaxation_parameters": [0.0, 1.2, 1.2, 1.5, 1.1],
+                }
+            ],
+            "init": init,
+            "boundary_conditions": {
+                0: {"method": {0: mod.bc.AntiBounceBack}, "value": (_t_wall, (1.0,))},
+                1: {"method": {0: mod.bc.AntiBounceBack}, "value": (_t_wall, (0.25,))},
+            },
+            "generator": generator,
+        }
     return {
         "box": {"x": [0.0, 1.0], "y": [0.0, 1.0], "label": [0, 1, 2, 3]},
         "elements": [

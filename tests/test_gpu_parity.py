@@ -260,7 +260,7 @@ def test_runtime_scalars_from_extra_parameters():
 
 @pytest.mark.parametrize("name,kw,dtype", [
     ("lid_cavity_d3q19", dict(n=16), "float64"), ("channel_sphere_d3q27", dict(nx=21, ny=13, nz=9), "float64"),
-    ("lid_cavity_d3q19", dict(n=12), "float32"),
+    ("lid_cavity_d3q19", dict(n=12), "float32"), ("heat_d2q5", dict(n=24, plain=True), "float64"),
 ])
 def test_walls_in_the_fused_kernel_are_bit_identical_to_the_list_kernel(name, kw, dtype, monkeypatch):
     """bounce-back walls normal to the fastest axis are applied by the fused kernel (lbmk_walls) when
@@ -292,6 +292,18 @@ def test_walls_in_the_fused_kernel_are_bit_identical_to_the_list_kernel(name, kw
     assert np.array_equal(a.container.F.get()[inner], b.container.F.get()[inner])
     for key in a.scheme.consm:
         assert np.array_equal(a.m[key], b.m[key])
+    if dtype == "float64":
+        # and both agree with the oracle
+        from oracle.lbm_oracle import OracleSimulation
+
+        ora = OracleSimulation(cases.CASES[name](perturb=0, **kw))
+        for _ in range(17):
+            ora.one_time_step()
+        fluid = ora.domain.in_or_out[tuple(slice(v, -v) for v in ora.domain.stencil.vmax)] == ora.domain.valin
+        for key in a.scheme.consm:
+            okey = [k for k in ora.scheme.consm if str(k) == str(key)][0]
+            err = np.abs(a.m[key][fluid] - ora.m[okey][fluid]).max() / np.abs(ora.m[okey][fluid]).max()
+            assert err <= TOL_F64, (str(key), err)
 
 
 def test_wall_plan_is_refused_when_it_would_change_results():
