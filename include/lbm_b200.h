@@ -17,6 +17,10 @@
  *                                                               678-680, 745-756, 818
  *   lbm_sim_add_bc / lbm_sim_set_rhs <- BoundaryMethod.move2gpu / set_rhs
  *                                                               boundary.py:378-397, 421-427
+ *   lbm_sim_bc_groups, lbm_sim_set_walls, lbm_sim_bc_stale_only
+ *                           <- the loop `for method in bc.methods: method.update(F)`
+ *                              (simulation.py:387-390) with fewer launches: merged methods, and
+ *                              plain bounce-back walls applied by the fused kernel itself
  *   lbm_array_h2d / lbm_array_d2h <- Array.__setitem__/__getitem__ device sync
  *                                                               storage.py:126-157
  *
