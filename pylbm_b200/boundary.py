@@ -33,6 +33,17 @@ __all__ = [
 ]
 
 
+def _member(sorted_values, x):
+    """boolean mask: x[i] is in `sorted_values` (ascending).  One binary search per query instead of
+    np.isin's sort of both arrays: the boundary lists of a 512^3 lattice have 8 M entries."""
+    x = np.asarray(x)
+    if sorted_values.size == 0 or x.size == 0:
+        return np.zeros(x.shape, dtype=bool)
+    idx = np.searchsorted(sorted_values, x)
+    idx[idx == sorted_values.size] = sorted_values.size - 1
+    return sorted_values[idx] == x
+
+
 def merge_groups(methods, max_group=12):
     """
     Greedy grouping of consecutive boundary methods into merged launches (lbm_sim_bc_groups).
@@ -161,28 +172,30 @@ def plan_walls(methods, array, velocities, symmetric):
     mine_store = np.concatenate([np.asarray(m["store"])[mask] for m, mask in zip(methods, masks)] + [empty])
     mine_owner = np.concatenate([np.full(int(mask.sum()), im) for im, mask in enumerate(masks)] + [empty])
     mine_load = np.concatenate([np.asarray(m["loads"][0])[mask] for m, mask in zip(methods, masks)] + [empty])
-    other_store = np.concatenate([np.asarray(m["store"])[~mask] for m, mask in zip(methods, masks)] + [empty])
-    if mine_store.size == 0 or np.unique(mine_store).size != mine_store.size:
-        return None
-    if np.isin(mine_store, other_store).any():
-        return None
-    if np.isin(mine_load, other_store).any() or np.isin(mine_load, mine_store).any():
-        return None
-    # what the kernel writes without a replaced entry behind it must be overwritten by the list
-    loose = written[~np.isin(written, mine_store)]
-    if not np.isin(loose, other_store).all():
+    other_store = np.sort(np.concatenate([np.asarray(m["store"])[~mask] for m, mask in zip(methods, masks)] + [empty]))
+    if mine_store.size == 0:
         return None
     order = np.argsort(mine_store)
     sorted_store, sorted_owner = mine_store[order], mine_owner[order]
+    if (sorted_store[1:] == sorted_store[:-1]).any():
+        return None
+    if _member(other_store, mine_store).any():
+        return None
+    if _member(other_store, mine_load).any() or _member(sorted_store, mine_load).any():
+        return None
+    # what the kernel writes without a replaced entry behind it must be overwritten by the list
+    loose = np.sort(written[~_member(sorted_store, written)])
+    if not _member(other_store, loose).all():
+        return None
     for im, (m, mask) in enumerate(zip(methods, masks)):
         for j, l in enumerate(m["loads"]):
             l = np.asarray(l)
             l = l[~mask] if j == 0 else l
             if l.size == 0:
                 continue
-            if np.isin(l, loose).any():
+            if _member(loose, l).any():
                 return None
-            hit = np.isin(l, mine_store)
+            hit = _member(sorted_store, l)
             if hit.any():                      # only later methods may read a replaced position
                 owner = sorted_owner[np.searchsorted(sorted_store, l[hit])]
                 if (owner >= im).any():
@@ -220,15 +233,15 @@ def schedule(store, loads, snapshot=False):
         # One level; it gathers before it scatters only if some entry reads a position the method stores.
         _, last = np.unique(store[::-1], return_index=True)
         order = np.sort(n - 1 - last)
-        st = store[order]
-        alias = any(np.isin(l[order], st).any() for l in loads)
+        st = np.sort(store[order])
+        alias = any(_member(st, l[order]).any() for l in loads)
         return order, np.array([0, order.size], dtype=np.int64), np.array([1 if alias else 0], dtype=np.int32)
 
+    sorted_store = np.sort(store)
     aliased = np.zeros(n, dtype=bool)          # entry reads something some entry stores
     for l in loads:
-        aliased |= np.isin(l, store)
-    uniq, counts = np.unique(store, return_counts=True)
-    dup_pos = uniq[counts > 1]
+        aliased |= _member(sorted_store, l)
+    dup_pos = np.unique(sorted_store[1:][sorted_store[1:] == sorted_store[:-1]])
     duplicated = np.isin(store, dup_pos) if dup_pos.size else np.zeros(n, dtype=bool)
 
     if aliased.any() or duplicated.any():
@@ -262,10 +275,13 @@ def schedule(store, loads, snapshot=False):
     level_ptr = np.zeros(nlev + 1, dtype=np.int64)
     np.cumsum(np.bincount(level, minlength=nlev), out=level_ptr[1:])
     two_phase = np.zeros(nlev, dtype=np.int32)
-    for l in range(nlev):
-        sel = order[level_ptr[l] : level_ptr[l + 1]]
-        st = store[sel]
-        two_phase[l] = int(any(np.isin(ld[sel], st).any() for ld in loads))
+    if nlev == 1:
+        two_phase[0] = int(aliased.any())      # one level: an entry reads a position the level stores
+    else:
+        for l in range(nlev):
+            sel = order[level_ptr[l] : level_ptr[l + 1]]
+            st = np.sort(store[sel])
+            two_phase[l] = int(any(_member(st, ld[sel]).any() for ld in loads))
     return order, level_ptr, two_phase
 
 
