@@ -578,7 +578,7 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
         if ((desc->periodic_mask & (1 << a)) && w > 0 && desc->grid.n[a] - 2 * w >= 2 * w) s->wrap_mask |= (1 << a);
     }
     if (getenv("PYLBM_B200_NO_ZWRAP")) s->wrap_mask &= ~(1 << 2);   // debugging aid: lean copy kernel for z
-    if (getenv("PYLBM_B200_NO_WRAP")) s->wrap_mask = 0;
+    if (getenv("PYLBM_B200_NO_WRAP")) s->wrap_mask = 0;             // debugging aid: copy kernels every step
     for (int a = 0; a < 3; ++a) {
         s->sel[a].n = 0;
         for (int k = 0; k < desc->nv; ++k) {
@@ -588,7 +588,7 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
             s->sel[a].side[s->sel[a].n] = (v > 0) ? 1 : 2;
             s->sel[a].n++;
         }
-    }   // debugging aid: use the copy kernels every step
+    }
     cudaError_t e = cudaStreamCreate(&s->stream);
     if (e == cudaSuccess) e = cudaStreamCreate(&s->comm_stream);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
@@ -655,29 +655,47 @@ extern "C" int lbm_sim_add_bc(lbm_sim* s, int kind, int64_t ncond, const int64_t
     BcMethod b;
     b.kind = kind;
     b.ncond = ncond;
-    CUDA_TRY(upload(&b.istore, (const long long*)istore, ncond));
-    CUDA_TRY(upload(&b.iload0, (const long long*)iload0, ncond));
-    CUDA_TRY(upload(&b.iload1, (const long long*)iload1, two_loads ? ncond : 0));
-    CUDA_TRY(upload(&b.rhs, rhs, kind != LBM_BC_NEUMANN ? ncond : 0));
-    CUDA_TRY(upload(&b.dist, dist, two_loads ? ncond : 0));
+    {
+        cudaError_t e = upload(&b.istore, (const long long*)istore, ncond);
+        if (e == cudaSuccess) e = upload(&b.iload0, (const long long*)iload0, ncond);
+        if (e == cudaSuccess) e = upload(&b.iload1, (const long long*)iload1, two_loads ? ncond : 0);
+        if (e == cudaSuccess) e = upload(&b.rhs, rhs, kind != LBM_BC_NEUMANN ? ncond : 0);
+        if (e == cudaSuccess) e = upload(&b.dist, dist, two_loads ? ncond : 0);
+        if (e != cudaSuccess) {
+            free_bc(b);
+            return set_error(-(int)e, "lbm_sim_add_bc", cudaGetErrorString(e));
+        }
+    }
     if (nlevels <= 0 || !level_ptr) {
         b.level_ptr = {0, (long long)ncond};
         b.two_phase = {kind == LBM_BC_BOUZIDI_BOUNCE_BACK ? 1 : 0};
     } else {
         b.level_ptr.assign(level_ptr, level_ptr + nlevels + 1);
         for (int i = 0; i < nlevels; ++i) b.two_phase.push_back(two_phase ? two_phase[i] : 1);
-        if (b.level_ptr.front() != 0 || b.level_ptr.back() != ncond) return ARG_ERROR("level_ptr must span [0, ncond]");
+        if (b.level_ptr.front() != 0 || b.level_ptr.back() != ncond) {
+            free_bc(b);
+            return ARG_ERROR("level_ptr must span [0, ncond]");
+        }
     }
     long long maxlevel = 0;
     for (size_t i = 0; i + 1 < b.level_ptr.size(); ++i) {
         long long n = b.level_ptr[i + 1] - b.level_ptr[i];
-        if (n < 0) return ARG_ERROR("level_ptr must be non-decreasing");
+        if (n < 0) {
+            free_bc(b);
+            return ARG_ERROR("level_ptr must be non-decreasing");
+        }
         if (n > maxlevel) maxlevel = n;
     }
     if (maxlevel > s->scratch_n) {
         cudaFree(s->scratch);
         s->scratch = nullptr;
-        CUDA_TRY(cudaMalloc(&s->scratch, (size_t)maxlevel * sizeof(double)));
+        s->scratch_n = 0;
+        cudaError_t e = cudaMalloc(&s->scratch, (size_t)maxlevel * sizeof(double));
+        if (e != cudaSuccess) {
+            s->scratch = nullptr;
+            free_bc(b);
+            return set_error(-(int)e, "lbm_sim_add_bc: scratch", cudaGetErrorString(e));
+        }
         s->scratch_n = maxlevel;
     }
     s->bcs.push_back(b);
