@@ -113,3 +113,56 @@ def test_same_structure_as_a_file_written_by_libhdf5(tmp_path):
     assert _structure(golden2)[1] == _structure(mine2)[1]
     for key, val in data2.items():
         assert np.array_equal(_reader()(mine2).datasets()[key], val)
+
+
+def test_h5file_gathers_slabs_on_rank_0(tmp_path):
+    """two ranks (threads here) own x-slabs; the parts reach rank 0 through the topology's all-gather
+    callable, like the reference's Send/Recv to rank 0 (hdf5.py:163-178)."""
+    import threading
+
+    from pylbm_b200.domain import SlabTopology
+    from pylbm_b200.hdf5 import H5File
+
+    world = 2
+    x = np.linspace(0.0, 1.0, 10)
+    y = np.linspace(0.0, 0.5, 4)
+    rng = np.random.default_rng(3)
+    field = rng.uniform(size=(10, 4))
+    cuts = [0, 6, 10]
+    box, lock, barrier = {}, threading.Lock(), threading.Barrier(world)
+    errors = []
+
+    def make_gather(rank):
+        def gather(obj):
+            with lock:
+                box[rank] = obj
+            barrier.wait()
+            out = [box[r] for r in range(world)]
+            barrier.wait()
+            return out
+        return gather
+
+    def worker(rank):
+        try:
+            topo = SlabTopology(2, rank, world)
+            topo.gather = make_gather(rank)
+            h5 = H5File(topo, "slabs", str(tmp_path))
+            sl = slice(cuts[rank], cuts[rank + 1])
+            h5.set_grid(x[sl], y)
+            h5.add_scalar("rho", field[sl])
+            h5.add_vector("q", [field[sl], 2 * field[sl]])
+            h5.save()
+        except Exception as exc:      # pragma: no cover
+            errors.append(exc)
+            barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(60)
+    assert not errors, errors
+    back = _reader()(str(tmp_path / "slabs.h5")).datasets()
+    assert np.array_equal(back["x_0"], x) and np.array_equal(back["x_1"], y)
+    assert np.array_equal(back["rho"], field.T)
+    assert np.array_equal(back["q"][..., 1], 2 * field.T) and not back["q"][..., 2].any()
