@@ -199,6 +199,17 @@ def main():
         manifest["files"][name] = {"case": case, "kwargs": kw, "source": "tests/reference/" + h5,
                                    "final_time": 0.5, "space_step": 1.0 / 64}
         print("converted:", name, {k: v.shape for k, v in fields.items()})
+    # the reference's domain goldens (tests/domain/data/*.npz: distance, flag, in_or_out of seven small
+    # 2-D geometries, tests/domain/test_domain2D.py:10-19) re-saved compressed
+    src = os.path.join(REFERENCE, "tests", "domain", "data")
+    dst = os.path.join(OUT, "domain")
+    os.makedirs(dst, exist_ok=True)
+    for fname in sorted(os.listdir(src)):
+        if fname.endswith(".npz"):
+            data = np.load(os.path.join(src, fname))
+            np.savez_compressed(os.path.join(dst, fname), **{k: data[k] for k in data.files})
+            manifest["files"]["domain/" + fname] = {"source": "tests/domain/data/" + fname}
+            print("copied:", fname, {k: data[k].shape for k in data.files})
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
 
