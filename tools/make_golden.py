@@ -210,6 +210,17 @@ def main():
             np.savez_compressed(os.path.join(dst, fname), **{k: data[k] for k in data.files})
             manifest["files"]["domain/" + fname] = {"source": "tests/domain/data/" + fname}
             print("copied:", fname, {k: data[k].shape for k in data.files})
+    # the reference's velocity tables D1Q2 ... D3Q27 (tests/conftest.py:19-163, the `_schemes` dict of its
+    # stencil fixtures), read from the source with ast (importing that conftest needs h5py)
+    import ast
+
+    tree = ast.parse(open(os.path.join(REFERENCE, "tests", "conftest.py")).read())
+    for node in tree.body:
+        if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", None) == "_schemes":
+            table = eval(compile(ast.Expression(node.value), "conftest", "eval"), {"list": list, "range": range})
+            with open(os.path.join(OUT, "stencils.json"), "w") as fh:
+                json.dump(table, fh, indent=0, sort_keys=True)
+            manifest["files"]["stencils.json"] = {"source": "tests/conftest.py:19-163"}
     with open(os.path.join(OUT, "MANIFEST.json"), "w") as fh:
         json.dump(manifest, fh, indent=1, sort_keys=True)
 
