@@ -105,3 +105,19 @@ def test_domain1d_two_schemes(labels):
     flag[(2, 4, 4), (2, 2, 3)] = lleft
     flag[(1, 3, 3), (-3, -3, -4)] = lright
     assert np.all(dom.flag == flag)
+
+
+@pytest.mark.parametrize("index", range(9))
+def test_domain_cases_of_the_reference_test_module(index):
+    """geometries of the reference's tests/test_domain.py (which only compares pictures): ellipse and
+    circle under D2Q13 (two ghost layers), labelled box faces, overlapping solid and fluid elements,
+    ellipsoid / sphere / plain box under D3Q19 -- fixtures from the unmodified reference
+    (tools/make_domain_golden.py)."""
+    import pylbm_b200 as lb
+    from domain_cases import domain_cases
+
+    ref = np.load(os.path.join(os.path.dirname(GOLDEN), "domain_cases.npz"))
+    dom = lb.Domain(domain_cases(lb)[index])
+    assert np.array_equal(dom.in_or_out, ref["c%d_in_or_out" % index])
+    assert np.array_equal(dom.flag, ref["c%d_flag" % index])
+    assert np.array_equal(dom.distance, ref["c%d_distance" % index])
