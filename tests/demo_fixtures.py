@@ -43,6 +43,8 @@ def load_demo(test, mod=None, generator="cuda"):
         import pylbm_b200 as mod
     with open(os.path.join(DEMOS, test + ".pkl"), "rb") as fh:
         record = pickle.load(fh)
+    if "early" in record:         # notebooks: the dictionary was pickled when the Simulation was built
+        record["dico"], record["sim_args"], record["sim_kwargs"] = pickle.loads(record["early"])
     dico = _resolve(record["dico"], mod)
     dico["generator"] = generator
     return dico, dict(record["sim_kwargs"]), record
