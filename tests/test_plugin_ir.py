@@ -124,3 +124,54 @@ def test_module_object_built_from_a_reference_simulation(pylbm):
         else:
             assert set(fn.arg_dict) <= wanted | {"dt", "t"}
     assert "lbmk_kernel_one_time_step" in module.source
+
+
+DEMO_SCHEMES = ["test1D_euler", "test1D_advection_reaction", "test2D_orszag_Tang_vortex", "test2D_shallow_water",
+                "test2D_kelvin_Helmoltz", "test2D_air_conditioning", "test3D_poseuille", "test3D_karman", "nb04_1"]
+
+
+@pytest.mark.parametrize("test", DEMO_SCHEMES)
+def test_reference_routines_of_the_demo_dictionaries(pylbm, test):
+    """the plugin path on the dictionaries of the reference's own demos / notebooks: the Routines the
+    REFERENCE's symbolic algorithm produces for them (vectorial schemes with up to six sub-schemes,
+    relative velocities, source terms, D3Q15) are lowered by plugin.routine_to_ir and evaluated with
+    NumPy; the result must equal the literal C restatement of the same scheme."""
+    from demo_fixtures import load_demo
+    from lowering_eval import evaluate
+    from pylbm_b200.plugin import routine_to_ir
+    from pylbm_b200.scheme import Scheme
+    from oracle.lbm_oracle import build_library
+
+    ref_dico, _, _ = load_demo(test, mod=pylbm, generator="cython")
+    ref_scheme, routines = _routines(pylbm, ref_dico)
+    ir = routine_to_ir(routines["one_time_step"])
+    our_dico, _, _ = load_demo(test)
+    scheme = Scheme(our_dico)
+    lib, extras = build_library(scheme)
+    assert not extras
+    dim, Q = scheme.dim, len(ir.in_syms)
+    assert Q == int(scheme.stencil.nv_ptr[-1])
+    vel = scheme.stencil.get_all_velocities()
+    assert [tuple(o) for o in ir.in_offsets] == [tuple(-int(c) for c in v) for v in vel]
+    vmax = list(scheme.stencil.vmax) + [0] * (3 - dim)
+    n = [4 + 2 * v for v in vmax[:dim]] + [1] * (3 - dim)
+    rng = np.random.default_rng(5)
+    f = 1.0 / Q + 0.01 * rng.uniform(-1, 1, size=tuple(n) + (Q,))
+    # vectorial schemes divide by their own density (h, rho): keep every sub-scheme's mass near one
+    nv_ptr = list(scheme.stencil.nv_ptr)
+    for a, b in zip(nv_ptr[:-1], nv_ptr[1:]):
+        f[..., a:b] *= Q / float(b - a)
+    fnew = np.zeros_like(f)
+    dt = 0.01
+    lib.one_time_step(f.ctypes.data_as(ctypes.c_void_p), fnew.ctypes.data_as(ctypes.c_void_p),
+                      *[ctypes.c_int(v) for v in n], ctypes.c_double(0.0), ctypes.c_double(dt),
+                      (ctypes.c_double * 1)(0.0))
+    inner = tuple(slice(v, nn - v) for v, nn in zip(vmax, n))
+    pulled = []
+    for k in range(Q):
+        off = list(ir.in_offsets[k]) + [0] * (3 - dim)
+        pulled.append(f[tuple(slice(v + o, nn - v + o) for v, nn, o in zip(vmax, n, off)) + (k,)])
+    out = evaluate(ir, pulled, {"dt": dt, "t": 0.0})
+    scale = max(np.abs(fnew[inner]).max(), 1.0)
+    err = max(np.abs(out[k] - fnew[inner + (k,)]).max() for k in range(Q))
+    assert err <= 1e-13 * scale, (test, err)
