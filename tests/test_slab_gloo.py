@@ -26,7 +26,14 @@ def _worker(rank, world, port, case, kw, nsteps, queue):
     from oracle.lbm_oracle import OracleSimulation
 
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    dico = cases.CASES[case](perturb=cases.WAVE, **kw)
+    final_time = None
+    if case.startswith("fixture:"):
+        from demo_fixtures import load_demo
+
+        dico, _, record = load_demo(case[len("fixture:"):])
+        final_time = record["final_time"]
+    else:
+        dico = cases.CASES[case](perturb=cases.WAVE, **kw)
     topo = SlabTopology(len(dico["box"]) - 1, rank, world)
     left, right = topo.left, topo.right
     vel = None
@@ -49,9 +56,14 @@ def _worker(rank, world, port, case, kw, nsteps, queue):
 
     sim = OracleSimulation(dico, topology=topo, exchange=exchange)
     vel = sim.scheme.stencil.get_all_velocities()
-    for _ in range(nsteps):
-        sim.one_time_step()
+    if final_time is not None:
+        while sim.t < final_time:          # the loop of the reference demos
+            sim.one_time_step()
+    else:
+        for _ in range(nsteps):
+            sim.one_time_step()
     out = {str(k): sim.m[k].copy() for k in sim.scheme.consm}
+    out["nt"] = sim.nt
     out["region"] = sim.domain.region[0]
     out["labels"] = sim.domain.box_label
     out["ncond"] = [int(m.istore.shape[0]) for m in sim.bc.methods]
@@ -93,3 +105,37 @@ def test_two_slabs_reproduce_one_rank(case, kw):
         assert whole.shape == full.shape
         scale = np.abs(full[fluid]).max()
         assert np.abs(whole[fluid] - full[fluid]).max() <= 1e-12 * max(scale, 1e-300)
+
+
+@pytest.mark.parametrize("test", ["test2D_rayleigh_benard", "test3D_poseuille", "test1D_euler", "test2D_coude"])
+def test_two_slabs_reproduce_the_reference_demo_fields(test):
+    """dictionaries of the reference's demo tests on two gloo ranks (x-slabs, oracle kernels, the
+    runtime's exchange protocol) against the fields of the unmodified single-rank reference:
+    time-dependent boundary values, vectorial schemes, 1-D and obstacles cut by nothing but the slabs."""
+    import torch.multiprocessing as mp
+
+    import pylbm_b200
+    from demo_fixtures import load_demo, load_results
+
+    world = 2
+    expected = load_results(test)
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, "fixture:" + test, {}, 0, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    dico, _, _ = load_demo(test)
+    domain = pylbm_b200.Domain(dico)
+    fluid = domain.in_or_out[tuple(slice(v, -v) for v in list(domain.stencil.vmax)[: domain.dim])] == domain.valin
+    for r in range(world):
+        assert results[r]["nt"] == expected["nsteps"]
+    for key, want in expected["ref"].items():
+        whole = np.concatenate([results[r][key] for r in range(world)], axis=0)
+        assert whole.shape == want.shape
+        err = np.abs(whole[fluid] - want[fluid]).max() / max(np.abs(want[fluid]).max(), 1e-300)
+        assert err <= 1e-12, (test, key, err)
