@@ -233,7 +233,8 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        res = cpu_reference_run((case_name, case_kw), args.steps, args.warmup, budget_s=90.0)
+        res = cpu_reference_run((case_name, case_kw), args.steps, args.warmup,
+                                budget_s=float(os.environ.get("PYLBM_B200_CPU_BUDGET_S", "90")))
         line = {
             "impl": "reference", "metric": "MLUPS", "value": res["value"], "unit": "MLUPS", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
