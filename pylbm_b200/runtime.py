@@ -8,6 +8,7 @@ fallback path in the product.
 
 import ctypes
 import json
+import os
 from ctypes import (
     POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_uint64, c_void_p,
 )
@@ -169,7 +170,10 @@ class _PinnedBlock:
 
     _pool = {}          # nbytes -> [ptr, ...]
     _pooled_bytes = 0
-    POOL_LIMIT = 16 << 30
+    try:                # at most 16 GB, and never more than a quarter of the host memory
+        POOL_LIMIT = min(16 << 30, os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") // 4)
+    except (ValueError, OSError, AttributeError):
+        POOL_LIMIT = 4 << 30
 
     def __init__(self, count):
         self.nbytes = int(count) * 8
