@@ -82,9 +82,11 @@ def _recursive_sub(expr, replace):
 class PullAlgorithm:
     """
     Builds the kernels of a scheme.  `settings` accepts the reference's keys
-    (m_local, split, check_isfluid); only the default fused, all-cells variant
-    is generated (the reference's Cython backend cannot print the `If` of
-    check_isfluid either, printing/cython.py:233-244).
+    (m_local, split, check_isfluid).  `m_local` and `split` only change how the
+    reference arranges its loops (one loop per statement over a global m array,
+    base.py:575-593), not what a cell computes: the fused kernel is generated
+    either way.  `check_isfluid` is refused (the reference's Cython backend
+    cannot print its `If` either, printing/cython.py:233-244).
     """
 
     def __init__(self, scheme, settings=None):
@@ -92,8 +94,8 @@ class PullAlgorithm:
         self.dim = scheme.dim
         self.ns = int(scheme.stencil.nv_ptr[-1])
         self.settings = settings or {}
-        if self.settings.get("check_isfluid", False) or self.settings.get("split", False):
-            raise NotImplementedError("check_isfluid / split are not supported by the CUDA backend")
+        if self.settings.get("check_isfluid", False):
+            raise NotImplementedError("check_isfluid is not supported by the CUDA backend")
         self.nconsm = len(scheme.consm)
         self.velocities = scheme.stencil.get_all_velocities()
 
