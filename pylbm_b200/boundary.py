@@ -25,6 +25,7 @@ import collections
 import numpy as np
 
 from . import runtime as rt
+from .domain import stencil_uvel
 from .storage import HostArray
 
 __all__ = [
@@ -296,7 +297,7 @@ class Boundary:
         self.domain = domain
         stencil = domain.stencil
         dico_bound = dico.get("boundary_conditions", {}) or {}
-        uvel = stencil.uvel
+        uvel = stencil_uvel(stencil)
 
         def entries(label, ku):
             # cells whose link along the symmetric of unique velocity ku is cut by `label`,
@@ -336,10 +337,26 @@ class Boundary:
                         distance[method] = np.concatenate([distance[method], dist])
 
         self.methods = [
-            method(istore[method], ilabel[method], distance[method], None, stencil, value_bc, time_bc,
-                   tuple([stencil.unvtot] + list(domain.shape_halo)), generator)
+            resolve_method(method)(istore[method], ilabel[method], distance[method], None, stencil, value_bc,
+                                   time_bc, tuple([stencil.unvtot] + list(domain.shape_halo)), generator)
             for method in istore
         ]
+
+
+def resolve_method(cls):
+    """boundary-method class of this package for a class given in a dictionary: itself, or -- for the
+    classes of an importable reference pylbm (`pylbm.bc.BounceBack`, ...) -- the class of the same name
+    (a user-defined subclass resolves through its first known base)."""
+    if isinstance(cls, type) and issubclass(cls, BoundaryMethod):
+        return cls
+    known = {c.__name__: c for c in (BounceBack, BouzidiBounceBack, AntiBounceBack, BouzidiAntiBounceBack,
+                                     Neumann, NeumannX, NeumannY, NeumannZ)}
+    for base in getattr(cls, "__mro__", ()):
+        if base.__name__ in known:
+            if base is not cls and any(name in vars(cls) for name in ("set_iload", "set_rhs", "generate", "update")):
+                break       # a user subclass that changes the lists or the kernel: not expressible here
+            return known[base.__name__]
+    raise NotImplementedError("boundary method %r has no CUDA implementation" % (cls,))
 
 
 class BoundaryMethod:
@@ -373,6 +390,10 @@ class BoundaryMethod:
     # ---- lists -------------------------------------------------------------
     def set_iload(self):
         raise NotImplementedError
+
+    def generate(self, sorder):
+        """the boundary kernels are part of the static runtime (k_bc<KIND>): nothing to generate
+        (reference: boundary.py:323-339 adds one routine per method)."""
 
     def fix_iload(self):
         """final (ncond, dim+1) int32 C-contiguous layout (reference: boundary.py:226-235)."""

@@ -31,6 +31,14 @@ from .stencil import Stencil
 __all__ = ["Domain", "SlabTopology"]
 
 
+def stencil_uvel(stencil):
+    """[unvtot, dim] integer array of the unique velocities (the reference's Stencil has uvx/uvy/uvz,
+    stencil.py:739-767)."""
+    if hasattr(stencil, "uvel"):
+        return np.asarray(stencil.uvel)
+    return np.asarray([stencil.uvx, stencil.uvy, stencil.uvz][: stencil.dim], dtype=np.int64).T.reshape(-1, stencil.dim)
+
+
 class SlabTopology:
     """
     1-D block decomposition along x over `size` ranks, periodic in every
@@ -107,9 +115,13 @@ class Domain:
     valin = 999
     valout = -1
 
-    def __init__(self, dico, need_validation=True, topology=None):
-        self.geom = Geometry(dico, need_validation=False)
-        self.stencil = Stencil(dico, need_validation=False)
+    def __init__(self, dico, need_validation=True, topology=None, geometry_cls=None, stencil_cls=None):
+        # `geometry_cls` / `stencil_cls`: the classes of an importable reference pylbm (plugin.py); the
+        # builder only uses their public attributes, and elements through get_bounds / point_inside /
+        # distance, so the reference's own elements (STL, cylinders, ...) work as they are
+        self.geom = (geometry_cls or Geometry)(dico, need_validation=False)
+        self.stencil = (stencil_cls or Stencil)(dico, need_validation=False)
+        self._uvel = stencil_uvel(self.stencil)
         self.dx = dico["space_step"]
         self.dim = self.geom.dim
         self.compute_normal = False
@@ -219,7 +231,7 @@ class Domain:
         inner = tuple(slice(h, -h) if h > 0 else slice(None) for h in halo)
         self.in_or_out[inner] = self.valin
 
-        uvel = self.stencil.uvel
+        uvel = self._uvel
         for k in range(self.stencil.unvtot):
             cand_cell, cand_dist, cand_flag = [], [], []
             for d in range(self.dim):
@@ -291,7 +303,7 @@ class Domain:
             ind_solid = np.logical_not(ind_fluid)
             ioo_view[ind_fluid] = self.valin
 
-        uvel = self.stencil.uvel
+        uvel = self._uvel
         for k in range(self.stencil.unvtot):
             vk = uvel[k]
             if not np.any(vk != 0):

@@ -1,29 +1,42 @@
 """
-Registration of `generator='cuda'` inside an importable reference pylbm.
+`generator='cuda'` inside an importable reference pylbm: the drop-in boundary of SURVEY.md 8(b).
 
-pylbm selects a backend by the string `dico['generator']` in four hard-coded tables
-(SURVEY.md 8b).  `register()` extends them at run time -- the reference tree is never edited:
+pylbm selects a backend by the string `dico['generator']` in hard-coded tables.  `register()` extends
+them at run time -- the reference tree is never edited:
 
-  1. validator          pylbm/validator.py:327-329      'cuda' admitted
-  2. container table    pylbm/simulation.py:165-171     "CUDA" -> CudaRefContainer (HBM-resident arrays)
-  3. code generator     pylbm/generator/codegen.py:1484-1494   "CUDA" -> CudaCodeGen
-  4. code wrapper       pylbm/generator/autowrap.py:155-163    "CUDA" -> CudaCodeWrapper
+  1. validator          pylbm/validator.py:327-329              'cuda' admitted
+  2. container table    pylbm/simulation.py:165-171             "CUDA" -> CudaContainer (padded SoA in HBM)
+  3. code generator     pylbm/generator/codegen.py:1484-1494    "CUDA" -> CudaCodeGen
+  4. code wrapper       pylbm/generator/autowrap.py:155-163     "CUDA" -> CudaCodeWrapper / Generator.compile
+  5. `pylbm.Simulation(dico)` with generator='cuda' instantiates `CudaSimulation`, a SUBCLASS of the
+     reference class (one `__new__` hook).  Its constructor IS the reference's constructor
+     (simulation.py:89-153, unchanged, called through super()): validate -> Domain -> Scheme -> Generator
+     -> container -> algorithm.generate() -> Boundary -> compile -> initialize.  Two names the constructor
+     resolves in its module are redirected for this backend: `Domain` builds the sparse records of
+     pylbm_b200.domain from the reference's own Geometry / Stencil / elements (the dense
+     [unvtot, nx, ny, nz] arrays of domain.py:285-293 are ~105 GB for D3Q19 at 512^3), and `Boundary`
+     builds the same ordered index lists from them (bit-identical, tests/test_gpu_plugin.py).
 
-After that the UNCHANGED `pylbm.Simulation(dico)` drives the CUDA kernels: its symbolic algorithm
-(`pylbm/algorithm/base.py:602-628` adds one `Routine` per kernel, a `For` over `Eq` statements on
-`Indexed` arrays) is lowered by `routine_to_ir()` into this package's per-cell IR and compiled by
-cudagen/nvcc; the boundary routines (`bounce_back`, `Bouzidi_bounce_back`, ...) are mapped by name to
-the runtime's boundary kernels.  The module-like object returned to the driver exposes one callable
-per routine with an `arg_dict` (the kwargs protocol of `pylbm/symbolic.py:288-299`).
+What the subclass overrides is the hot path (CudaEngine): `one_time_step()` is ONE enqueue-only runtime
+call (`lbm_sim_step`: ghost update, boundary kernels over device-resident lists uploaded once, fused
+pull kernel, swap), `boundary_condition()` one `lbm_sim_boundary_condition`; nothing is allocated,
+copied or synchronised per step.  `sol.m[...]`, `sol.F[...]`, `f2m/m2f/equilibrium/relaxation/
+transport/source_term`, `sol.t/nt/dt`, `extra_parameters` keep the reference's meaning.
 
-This is the compatibility path: every piece of the reference's per-step Python still runs (ghost
-update, set_rhs, one call per boundary method, kernel, swap).  The fast path -- one runtime call per
-step -- is `pylbm_b200.Simulation`.
+Kernels.  Two lowerings produce the per-scheme CUDA library, both compiled by cudagen/nvcc:
+  * 'scheme' (default for the stock PullAlgorithm): the scheme-level lowering of algorithm.py (numeric
+    transforms + sparse relative-velocity shifts; 2x fewer fp64 operations than the reference's dense
+    polynomial matrices when `relative_velocity` is used);
+  * 'ir' (`dico['cuda_option'] = {'lowering': 'ir'}`, and always for a user-defined algorithm class): the
+    reference's own symbolic Routines (algorithm/base.py:602-628: a `For` over `Eq` statements on
+    `Indexed` arrays) are lowered statement by statement by `routine_to_ir()`.
+Either way the module-like object handed back to the reference (`sol.generator.module`) exposes one
+callable per routine with an `arg_dict` (the kwargs protocol of pylbm/symbolic.py:288-299), so
+`sol.algo.call_function(name, sol)` keeps working.
 
-Status: the IR lowering is tested on the CPU against the CPU checker whenever the reference is importable
-(tests/test_plugin_ir.py); the device classes need pylbm AND a GPU in the same process, which the
-GPU box of this project does not offer (no pylbm there), so they are exercised only to the point of
-the first device allocation.
+Multi-GPU: one process per GPU.  When `torch.distributed` is initialised with more than one rank (the
+role MPI.COMM_WORLD plays in the reference, mpi_topology.py:74-105) the lattice is cut into x-slabs,
+one per rank, with the fused NVLink halo; `configure()` overrides the discovery.
 """
 
 import ctypes
@@ -33,8 +46,9 @@ import sympy as sp
 
 from . import runtime as rt
 from .algorithm import KernelIR
+from .storage import DeviceView
 
-__all__ = ["register", "routine_to_ir", "BC_ROUTINES"]
+__all__ = ["register", "configure", "routine_to_ir", "build_ir_library", "CudaModule", "BC_ROUTINES"]
 
 BC_ROUTINES = {
     "bounce_back": rt.BC_BOUNCE_BACK,
@@ -176,170 +190,133 @@ def routine_to_ir(routine):
 
 
 # ---------------------------------------------------------------------------
-# device arrays seen through the reference's Array interface
-# ---------------------------------------------------------------------------
-class _Handle:
-    """what the driver passes around as `Array.array` (storage.py:107-118)."""
-
-    def __init__(self, dev):
-        self.dev = dev
-
-    def __getitem__(self, key):
-        return self
-
-    def __setitem__(self, key, other):      # Fnew.array[:] = F.array[:]  (simulation.py:320)
-        if isinstance(other, _Handle):
-            self.dev.copy_from(other.dev)
-        else:
-            self.dev.set(np.asarray(other))
-
-    def copy(self):                          # fcopy = F.array.copy()  (boundary.py:549): the Bouzidi
-        return self                          # kernel gathers before it scatters, no snapshot needed
-
-    shape = property(lambda self: self.dev.shape)
-    size = property(lambda self: self.dev.size)
-
-
-class CudaRefArray:
-    """pylbm.storage.Array look-alike over a padded SoA DeviceArray."""
-
-    gpu_support = False      # keeps the reference away from its pyopencl branches (storage.py:109-157)
-
-    def __init__(self, nv, shape_halo, vmax, consm=None):
-        from .storage import DeviceArray
-
-        self.dev = DeviceArray(nv, shape_halo, vmax, "f64", consm)
-        self.array = _Handle(self.dev)
-        self.vmax = list(vmax)
-        self.consm = self.dev.consm
-        self.sorder = self.index = list(range(len(shape_halo) + 1))
-        self.dim = len(shape_halo)
-
-    nspace = property(lambda self: self.dev.nspace)
-    nv = property(lambda self: self.dev.nv)
-    shape = property(lambda self: self.dev.shape)
-    size = property(lambda self: self.dev.size)
-    swaparray = property(lambda self: self.dev.get())
-
-    def set_conserved_moments(self, consm):
-        self.dev.set_conserved_moments(consm)
-
-    def __getitem__(self, key):
-        return self.dev[key]
-
-    def __setitem__(self, key, values):
-        self.dev[key] = values
-
-    def _in(self, key):
-        return self.dev._in(key)
-
-    def generate(self, generator):
-        pass
-
-    def update(self):
-        """ghost update of one rank (storage.py:306-367)."""
-        vmax = (ctypes.c_int * 3)(*self.dev.canonical_vmax)
-        mask = sum(1 << a for a in range(3) if self.dev.canonical_vmax[a] > 0)
-        rt.check(
-            rt.lib().lbm_periodic(self.dev.ptr, ctypes.byref(self.dev.grid), self.dev.nv, self.dev.storage_id,
-                                  vmax, mask, None),
-            "lbm_periodic",
-        )
-
-
-class CudaRefContainer:
-    """the 'CUDA' entry of simulation.py:165-171."""
-
-    gpu_support = False
-
-    def __init__(self, domain, scheme, sorder=None):
-        self.dim = domain.dim
-        self.mpi_topo = domain.mpi_topo
-        self.nv = int(scheme.stencil.nv_ptr[-1])
-        self.nspace = domain.global_size
-        self.vmax = list(domain.stencil.vmax)
-        self.sorder = list(range(self.dim + 1))
-        shape = domain.shape_halo
-        self.m = CudaRefArray(self.nv, shape, self.vmax, scheme.consm)
-        self.F = CudaRefArray(self.nv, shape, self.vmax, scheme.consm)
-        self.Fnew = CudaRefArray(self.nv, shape, self.vmax, scheme.consm)
-
-    def move2gpu(self, array):
-        return array
-
-
-# ---------------------------------------------------------------------------
 # module-like object returned to the driver
 # ---------------------------------------------------------------------------
 class CudaModule:
-    def __init__(self, routines, dim_hint=None):
-        from . import build
-        from .cudagen import generate_source
+    """
+    What `Generator.compile()` leaves in `generator.module` for backend "CUDA" (the extension module
+    of autowrap.py:52-139): `.library` is the per-scheme kernel library (runtime.KernelLibrary), and
+    every routine name is a callable following the kwargs protocol.
+    `context` = {"dico", "algo", "storage", "compute", "lowering", "nv", "dim", "symmetric"} given by CudaSimulation;
+    without it (a bare `autowrap(routines, 'cuda')`) the routines are lowered from their IR in fp64.
+    """
 
-        kernels, self._bc = [], {}
-        for r in routines:
-            if r.name in BC_ROUTINES:
-                self._bc[r.name] = BC_ROUTINES[r.name]
-            else:
-                kernels.append(routine_to_ir(r))
+    def __init__(self, routines, context=None, verbose=False, directory=None):
+        context = context or {}
+        self._context = context
+        self._bc = {r.name: BC_ROUTINES[r.name] for r in routines if r.name in BC_ROUTINES}
+        self._cell_routines = [r for r in routines if r.name not in BC_ROUTINES]
         self._device_lists = {}
-        self._scratch = None
-        if kernels:
-            dim = len(kernels[0].in_offsets[0])
-            nv = len(kernels[0].in_syms)
-            source, info = generate_source(kernels, dim, nv)
-            self.library = rt.KernelLibrary(build.build_kernels(source, info["hash"]))
-            self.source = source
-            for ir in kernels:
-                setattr(self, ir.name, self._kernel(ir))
+        self.lowering = context.get("lowering") or "ir"
+        self.source = None
+        self.library = self.build(context.get("storage", "f64"), context.get("compute", "f64"),
+                                  need_source=bool(verbose or directory))
+        if verbose and self.source:
+            print(self.source)
+        if directory and self.source:
+            import os
+
+            os.makedirs(directory, exist_ok=True)
+            with open(os.path.join(directory, os.path.basename(self.library.path)[3:-3] + ".cu"), "w") as fh:
+                fh.write(self.source)
+        if self.library is not None:
+            for name in self.library.info["routines"]:
+                setattr(self, name, self._kernel(name))
         for name, kind in self._bc.items():
             setattr(self, name, self._boundary(name, kind))
 
-    # ---- per-cell kernels ----
-    def _kernel(self, ir):
-        lib, scalars = self.library, list(ir.scalars)
-        in_name, out_name = ir.in_array, ir.out_array
+    # ---- lowering ----
+    def _ir_kernels(self):
+        kernels = [routine_to_ir(r) for r in self._cell_routines]
+        by_name = {k.name: k for k in kernels}
+        nconsm = self._context.get("nconsm")
+        if "f2m" in by_name and nconsm and "f2m_consm" not in by_name:
+            f2m = by_name["f2m"]         # conserved rows only: what `sol.m[symbol]` reads after a step
+            kernels.append(KernelIR("f2m_consm", f2m.in_array, f2m.in_syms, f2m.in_offsets, f2m.out_array,
+                                    f2m.statements, f2m.outputs[:nconsm], False, f2m.scalars))
+        if "one_time_step" in by_name and self._context.get("symmetric") is not None:
+            by_name["one_time_step"].symmetric = [int(k) for k in self._context["symmetric"]]
+        return kernels
+
+    def build(self, storage="f64", compute="f64", need_source=False):
+        from . import build
+        from .cudagen import generate_source
+
+        if self.lowering == "scheme":
+            from .simulation import build_kernel_library
+
+            _, path, source = build_kernel_library(self._context["scheme"], self._context.get("settings"), storage,
+                                                   need_source=need_source, compute=compute)
+            self.source = source or self.source
+            return rt.KernelLibrary(path)
+        kernels = self._ir_kernels()
+        if not kernels:
+            return None
+        dim = len(kernels[0].in_offsets[0])
+        nv = len(kernels[0].in_syms)
+        c_type = {"f64": "double", "f32": "float"}
+        source, info = generate_source(kernels, dim, nv, storage=c_type[storage], compute=c_type[compute])
+        self.source = source
+        return rt.KernelLibrary(build.build_kernels(source, info["hash"]))
+
+    # ---- per-cell kernels: kwargs protocol of symbolic.py:288-299 ----
+    def _kernel(self, name):
+        lib = self.library
+        info = lib.info["routines"][name]
+        scalars = list(info["scalars"])
+        in_name, out_name = info.get("in", "f"), info.get("out", "fnew")
+        inner = bool(info.get("inner", False))
 
         def call(queue=None, **kw):
             src, dst = kw[in_name], kw[out_name]
             values = [float(kw[s]) for s in scalars]
-            if isinstance(src, _Handle):
-                grid = src.dev.inner_grid() if ir.inner else src.dev.grid
-                lib.launch(ir.name, src.dev.ptr, dst.dev.ptr, grid, values)
+            if isinstance(src, DeviceView):
+                grid = src.dev.inner_grid() if inner else src.dev.grid
+                rt.check(rt.lib().lbm_device_sync(), "sync")      # the steps run on the simulation's stream
+                lib.launch(name, src.dev.ptr, dst.dev.ptr, grid, values)
                 rt.check(rt.lib().lbm_device_sync(), "sync")
                 return
             # small host arrays [nv, n, 1(, 1)] (wall equilibria: boundary.py:275-293)
             from .storage import DeviceArray
 
+            if lib.info.get("storage", "double") != "double":
+                raise NotImplementedError("host-array calls need the fp64 kernel library")
             ncell = int(np.prod(src.shape[1:]))
             dsrc = DeviceArray(src.shape[0], (ncell,), [0], "f64")
             dsrc.set(np.ascontiguousarray(src).reshape(src.shape[0], ncell))
             ddst = dsrc if dst is src else DeviceArray(dst.shape[0], (ncell,), [0], "f64")
-            lib.launch(ir.name, dsrc.ptr, ddst.ptr, dsrc.grid, values)
+            lib.launch(name, dsrc.ptr, ddst.ptr, dsrc.grid, values)
             rt.check(rt.lib().lbm_device_sync(), "sync")
             dst[...] = ddst.get().reshape(dst.shape)
 
         call.arg_dict = {k: None for k in dict.fromkeys([in_name, out_name] + scalars)}
-        call.__name__ = ir.name
+        call.__name__ = name
         return call
 
-    # ---- boundary kernels ----
-    def _positions(self, handle, index):
-        key = (index.ctypes.data, index.shape)
+    # ---- boundary kernels (compatibility protocol: `BoundaryMethod.update` of the reference calls
+    #      them every step with host lists; CudaSimulation never does, its lists live on the device) ----
+    def _cached(self, key, make):
         if key not in self._device_lists:
-            pos = np.ascontiguousarray(handle.dev.positions(index.T))
+            host = make()
             ptr = ctypes.c_void_p()
-            rt.check(rt.lib().lbm_malloc(ctypes.byref(ptr), max(8, pos.nbytes)), "lbm_malloc")
-            rt.check(rt.lib().lbm_memcpy_h2d(ptr, pos.ctypes.data, pos.nbytes), "h2d")
-            self._device_lists[key] = ptr.value
-        return self._device_lists[key]
+            rt.check(rt.lib().lbm_malloc(ctypes.byref(ptr), max(8, host.nbytes)), "lbm_malloc")
+            rt.check(rt.lib().lbm_memcpy_h2d(ptr, host.ctypes.data, host.nbytes), "h2d")
+            self._device_lists[key] = (ptr.value, host.nbytes)
+        return self._device_lists[key][0]
 
-    def _upload(self, array):
+    def _positions(self, view, index):
+        return self._cached(("pos", index.ctypes.data, index.shape),
+                            lambda: np.ascontiguousarray(view.dev.positions(index.T)))
+
+    def _values(self, tag, array, refresh):
+        """fp64 list kept on the device; the buffer is reused, the content refreshed when asked."""
         array = np.ascontiguousarray(array, dtype=np.float64)
-        ptr = ctypes.c_void_p()
-        rt.check(rt.lib().lbm_malloc(ctypes.byref(ptr), max(8, array.nbytes)), "lbm_malloc")
-        rt.check(rt.lib().lbm_memcpy_h2d(ptr, array.ctypes.data, array.nbytes), "h2d")
-        return ptr.value
+        key = (tag, array.ctypes.data, array.shape)
+        fresh = key not in self._device_lists
+        ptr = self._cached(key, lambda: array)
+        if refresh and not fresh:
+            rt.check(rt.lib().lbm_memcpy_h2d(ptr, array.ctypes.data, array.nbytes), "h2d")
+        return ptr
 
     def _boundary(self, name, kind):
         two_loads = kind in (rt.BC_BOUZIDI_BOUNCE_BACK, rt.BC_BOUZIDI_ANTI_BOUNCE_BACK)
@@ -356,44 +333,107 @@ class CudaModule:
             store = self._positions(f, kw["istore"])
             l0 = self._positions(f, kw["iload0"])
             l1 = self._positions(f, kw["iload1"]) if two_loads else None
-            rhs = self._upload(kw["rhs"]) if kind != rt.BC_NEUMANN else None
-            dist = self._upload(kw["dist"]) if two_loads else None
-            scratch = self._upload(np.zeros(ncond))
+            rhs = self._values("rhs", kw["rhs"], True) if kind != rt.BC_NEUMANN else None
+            dist = self._values("dist", kw["dist"], False) if two_loads else None
+            scratch = self._cached(("scratch", ncond), lambda: np.zeros(ncond))
             # the reference loop is sequential: gather-then-scatter keeps its result unless an entry
-            # reads what an EARLIER entry of the same call stored (see boundary.schedule); the
-            # stand-alone Simulation handles that case with levels
+            # reads what an EARLIER entry of the same call stored (boundary.schedule handles that case
+            # in CudaSimulation)
             rc = rt.lib().lbm_bc_apply(kind, f.dev.ptr, f.dev.storage_id, ncond, store, l0, l1, rhs, dist,
                                        scratch, 1, None)
             rt.check(rc, "lbm_bc_apply(%s)" % name)
-            rt.check(rt.lib().lbm_device_sync(), "sync")
-            for ptr in (rhs, dist, scratch):
-                if ptr:
-                    rt.lib().lbm_free(ptr)
 
         call.arg_dict = {k: None for k in names}
         call.__name__ = name
         return call
 
+    def __del__(self):
+        for ptr, _ in getattr(self, "_device_lists", {}).values():
+            try:
+                rt.lib().lbm_free(ptr)
+            except Exception:
+                pass
+
+
+# ---------------------------------------------------------------------------
+# process group discovery (the role of MPI.COMM_WORLD in the reference)
+# ---------------------------------------------------------------------------
+_config = {"slab": None, "nccl_id": None, "gather": None, "halo": "peer", "compute_dtype": None, "lowering": None}
+_pending = []       # context of the CudaSimulation under construction, read by the Domain factory
+
+
+def configure(**kwargs):
+    """
+    Process-wide settings of the CUDA backend (none is needed on one GPU):
+      slab=(rank, nranks), nccl_id=bytes, gather=callable   explicit x-slab decomposition instead of the
+                                                            torch.distributed discovery
+      halo='peer' | 'nccl'                                  fused NVLink halo (default) or NCCL send/recv
+      compute_dtype='float32'                               fp32 arithmetic (with dtype='float32')
+      lowering='scheme' | 'ir'                              see the module docstring
+    The last two can also be given per simulation as `dico['cuda_option'] = {'compute_dtype': ..,
+    'lowering': ..}` (the only key this backend adds to the reference's dictionary).
+    """
+    for key, value in kwargs.items():
+        if key not in _config:
+            raise KeyError("unknown setting %r" % key)
+        _config[key] = value
+
+
+def _process_group():
+    """(slab, nccl_id, gather) of this process."""
+    if _config["slab"] is not None:
+        return _config["slab"], _config["nccl_id"], (_config["gather"] if _config["halo"] == "peer" else None)
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None, None, None
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+        return None, None, None
+    rank, world = dist.get_rank(), dist.get_world_size()
+    box = [None]
+    if rank == 0:
+        raw = (ctypes.c_char * 128)()
+        rt.check(rt.lib().lbm_comm_unique_id(raw), "lbm_comm_unique_id")
+        box[0] = bytes(raw.raw)
+    dist.broadcast_object_list(box, src=0)
+
+    def gather(blob):
+        out = [None] * world
+        dist.all_gather_object(out, blob)
+        return out
+
+    return (rank, world), box[0], (gather if _config["halo"] == "peer" else None)
+
 
 # ---------------------------------------------------------------------------
 # registration
 # ---------------------------------------------------------------------------
-_registered = False
+_registered = None
+
+
+def _is_cuda(dico):
+    return str(dico.get("generator", "")).upper() == "CUDA"
 
 
 def register():
-    """make `generator='cuda'` known to the importable pylbm (idempotent)."""
+    """make `generator='cuda'` known to the importable pylbm (idempotent); returns the pylbm module."""
     global _registered
-    if _registered:
-        return
+    if _registered is not None:
+        return _registered
     import importlib
 
     import pylbm
+
+    from . import domain as b200_domain
+    from . import boundary as b200_boundary
+    from .simulation import CudaContainer, CudaEngine
 
     # (pylbm.generator re-exports functions named like its sub-modules: go through importlib)
     ref_simulation = importlib.import_module("pylbm.simulation")
     ref_autowrap = importlib.import_module("pylbm.generator.autowrap")
     ref_codegen = importlib.import_module("pylbm.generator.codegen")
+    ref_generator = importlib.import_module("pylbm.generator.generator")
+    RefSimulation = ref_simulation.Simulation
 
     # 3. code generator: the reference's CodeGen.routine() is backend independent
     #    (codegen.py:763-897); only `has_output` and the printer matter to it
@@ -413,13 +453,10 @@ def register():
     # 4. code wrapper (autowrap.py:52-76 contract: wrap_code(routines) -> module-like object)
     class CudaCodeWrapper:
         def __init__(self, generator, filepath=None, flags=(), generate=True, verbose=False):
-            self.verbose = verbose
+            self.verbose, self.filepath = verbose, filepath
 
         def wrap_code(self, routines):
-            module = CudaModule(list(routines))
-            if self.verbose:
-                print(module.source)
-            return module
+            return CudaModule(list(routines), None, self.verbose, self.filepath)
 
     original_wrapper = ref_autowrap.get_code_wrapper
 
@@ -430,27 +467,29 @@ def register():
 
     ref_autowrap.get_code_wrapper = get_code_wrapper
 
-    # 2. container table (simulation.py:165-171)
-    original_container = ref_simulation.Simulation._get_container
+    #    Generator.compile (generator.py:27-34) calls autowrap with the routines only; the CUDA module
+    #    also wants to know the storage type and the scheme, which the Simulation left on the generator
+    original_compile = ref_generator.Generator.compile
 
-    def _get_container(self, sorder):
-        if self.generator.backend == "CUDA":
-            rt.ensure_gpu()
-            return CudaRefContainer(self.domain, self.scheme, sorder)
-        return original_container(self, sorder)
+    def compile(self):
+        if str(self.backend).upper() == "CUDA":
+            self.module = CudaModule(list(self.routines.values()), getattr(self, "cuda_context", None),
+                                     self.verbose, self.directory)
+            return
+        original_compile(self)
 
-    ref_simulation.Simulation._get_container = _get_container
+    ref_generator.Generator.compile = compile
 
-    # 1. validator (validator.py:327-329): accept the new name when cerberus is the real one
+    # 1. validator (validator.py:327-329): accept the new name
     try:
         ref_validator = importlib.import_module("pylbm.validator")
-
         original_validate = ref_validator.validate
 
         def validate(dico, name):
-            if str(dico.get("generator", "")).lower() == "cuda":
+            if _is_cuda(dico):
                 patched = dict(dico)
                 patched["generator"] = "cython"
+                patched.pop("cuda_option", None)
                 return original_validate(patched, name)
             return original_validate(dico, name)
 
@@ -458,5 +497,127 @@ def register():
         ref_simulation.validate = validate
     except Exception:       # pragma: no cover
         pass
-    _registered = True
+
+    # 5. the two names the constructor resolves in its own module (simulation.py:94,136)
+    RefDomain, RefBoundary = ref_simulation.Domain, ref_simulation.Boundary
+
+    def Domain(dico, need_validation=True):
+        if _is_cuda(dico):
+            topology = _pending[-1].get("topology") if _pending else None
+            return b200_domain.Domain(dico, need_validation=False, topology=topology,
+                                      geometry_cls=pylbm.Geometry, stencil_cls=pylbm.Stencil)
+        return RefDomain(dico, need_validation=need_validation)
+
+    def Boundary(domain, generator, dico):
+        if str(getattr(generator, "backend", "")).upper() == "CUDA":
+            return b200_boundary.Boundary(domain, generator, dico)
+        return RefBoundary(domain, generator, dico)
+
+    ref_simulation.Domain = Domain
+    ref_simulation.Boundary = Boundary
+
+    class CudaSimulation(CudaEngine, RefSimulation):
+        """`pylbm.Simulation(dico)` for generator='cuda' (see the module docstring)."""
+
+        def __init__(self, dico, sorder=None, dtype="float64", check_inverse=False, initialize=True):
+            rt.ensure_gpu()
+            option = dico.get("cuda_option") or {}
+            storage, compute = self._storage_names(dtype, option.get("compute_dtype", _config["compute_dtype"]))
+            slab, nccl_id, gather = _process_group()
+            self._engine_defaults(storage, compute, slab, nccl_id, gather)
+            self._lowering = option.get("lowering", _config["lowering"])
+            topology = None
+            if self.nranks > 1:
+                topology = b200_domain.SlabTopology(pylbm.Stencil.extract_dim(dico), self.rank, self.nranks)
+                topology.gather = gather
+            _pending.append({"topology": topology})
+            try:
+                RefSimulation.__init__(self, dico, sorder, dtype, check_inverse, initialize)
+            finally:
+                _pending.pop()
+
+        # container table (simulation.py:165-171)
+        def _get_container(self, sorder):
+            return CudaContainer(self.domain, self.scheme, sorder, self.storage)
+
+        # algorithm (simulation.py:179-190): unchanged, but the generator learns what it compiles for
+        def _get_algorithm(self, dico, sorder):
+            algo = RefSimulation._get_algorithm(self, dico, sorder)
+            stock = type(algo) is importlib.import_module("pylbm.algorithm").PullAlgorithm
+            lowering = self._lowering or ("scheme" if stock else "ir")
+            if lowering not in ("scheme", "ir"):
+                raise ValueError("cuda_option['lowering'] must be 'scheme' or 'ir', got %r" % (lowering,))
+            if lowering == "scheme" and not stock:
+                raise ValueError("cuda_option['lowering']='scheme' only knows the stock PullAlgorithm")
+            context = {"storage": self.storage, "compute": self.compute, "lowering": lowering,
+                       "nconsm": len(self.scheme.consm), "symmetric": self.scheme.stencil.get_symmetric(),
+                       "settings": dict(algo.settings) if hasattr(algo, "settings") else None}
+            if lowering == "scheme":
+                context["scheme"] = _scheme_twin(dico, self.scheme)
+            self.generator.cuda_context = context
+            return algo
+
+        kernels = property(lambda self: self.generator.module.library)
+
+        def _build_kernels(self, storage, compute):
+            return self.generator.module.build(storage, compute)
+
+        def __repr__(self):
+            return RefSimulation.__str__(self)
+
+        __str__ = __repr__
+
+    CudaSimulation.__module__ = __name__
+    CudaSimulation.__qualname__ = "CudaSimulation"
+
+    def __new__(cls, dico=None, *args, **kwargs):
+        if cls is RefSimulation and isinstance(dico, dict) and _is_cuda(dico):
+            return object.__new__(CudaSimulation)
+        return object.__new__(cls)
+
+    RefSimulation.__new__ = staticmethod(__new__)
+    globals()["CudaSimulation"] = CudaSimulation
+    _registered = pylbm
     return pylbm
+
+
+def build_ir_library(dico, storage="f64", compute="f64"):
+    """
+    The kernel library of a dictionary lowered from the reference's own Routines, without touching a
+    device: what `pylbm.Simulation(dico)` with `cuda_option={'lowering': 'ir'}` compiles.  Used by the
+    build box (`__graft_entry__.build()`) to fill the in-tree cache.  Returns the CudaModule.
+    """
+    import importlib
+
+    pylbm = register()
+    generator_cls = importlib.import_module("pylbm.generator.generator").Generator
+    algo_cls = importlib.import_module("pylbm.algorithm").PullAlgorithm
+    scheme = pylbm.Scheme(dico)
+    generator = generator_cls("CUDA")
+    algo_cls(scheme, list(range(scheme.dim + 1)), generator,
+             {"m_local": True, "split": False, "check_isfluid": False}).generate()
+    context = {"storage": storage, "compute": compute, "lowering": "ir", "nconsm": len(scheme.consm),
+               "symmetric": scheme.stencil.get_symmetric()}
+    return CudaModule(list(generator.routines.values()), context)
+
+
+def _scheme_twin(dico, ref_scheme):
+    """
+    Numeric twin of the reference Scheme for the scheme-level lowering (exact rational M and inverse,
+    parameters substituted), built from the same dictionary and cross-checked against the reference's
+    object: same populations, same conserved moments at the same rows, same moment matrix.
+    """
+    from .scheme import Scheme
+
+    twin = Scheme(dico, need_validation=False)
+    ref_consm = {str(k): int(v) for k, v in ref_scheme.consm.items()}
+    if {str(k): int(v) for k, v in twin.consm.items()} != ref_consm:
+        raise rt.LbmError("scheme lowering: conserved moments differ from the reference's (%s)" % ref_consm)
+    if int(twin.stencil.nv_ptr[-1]) != int(ref_scheme.stencil.nv_ptr[-1]):
+        raise rt.LbmError("scheme lowering: number of populations differs from the reference's")
+    ref_M = sp.Matrix(ref_scheme.M).subs(list(ref_scheme.param.items()))
+    M = np.array(ref_M.evalf(), dtype=np.float64)
+    mine = np.array(sp.Matrix(twin.M).evalf(), dtype=np.float64)
+    if M.shape != mine.shape or not np.allclose(M, mine, rtol=1e-13, atol=1e-13):
+        raise rt.LbmError("scheme lowering: moment matrix differs from the reference's")
+    return twin

@@ -34,7 +34,7 @@ from .domain import Domain, SlabTopology
 from .scheme import Scheme
 from .storage import DeviceArray
 
-__all__ = ["Simulation", "CudaContainer"]
+__all__ = ["Simulation", "CudaEngine", "CudaContainer"]
 
 
 def build_kernel_library(scheme, settings=None, storage="f64", need_source=False, compute="f64"):
@@ -107,106 +107,51 @@ class CudaContainer:
             self._mc = DeviceArray(len(self._consm), self._shape, self.vmax, "f64", self._consm, align=self.F.align)
         return self._mc
 
+    def move2gpu(self, array):
+        """host arrays of the front end stay where they are: what the kernels need of them (boundary
+        lists) is uploaded once by BoundaryMethod.move2gpu (reference: container.py:100-106)."""
+        return array
+
     def release_m(self):
         """free the moment array (it is rebuilt by f2m on the next `sol.m[...]`)."""
         self._m = None
 
 
-class Simulation:
+class CudaEngine:
     """
-    Simulation(dico, sorder=None, dtype='float64', check_inverse=False, initialize=True,
-               slab=None, nccl_id=None, gather=None, compute_dtype=None)
-
-    `dico` is a pylbm dictionary (box, elements, space_step, scheme_velocity, schemes,
-    parameters, relative_velocity, init, inittype, boundary_conditions, generator,
-    codegen_option, lbm_algorithm, show_code).  `dtype='float32'` selects fp32 STORAGE of
-    the populations (arithmetic stays fp64) -- new functionality, the reference ignores
-    its dtype argument (simulation.py:89-91, storage.py:67).  `compute_dtype='float32'` (only with
-    dtype='float32') also runs the time-step kernels in fp32 arithmetic: the all-single-precision
-    mode, tolerance stated in tests/test_gpu_parity.py; moments (`sol.m`), initialisation and wall
-    equilibria are always computed in fp64.
-    `slab=(rank, nranks)` + `nccl_id` run this process as one x-slab of a multi-GPU run (NCCL
-    send/recv halo).  `gather(bytes) -> [bytes of every rank]` (an all-gather provided by the caller,
-    e.g. torch.distributed.all_gather_object) additionally enables the direct NVLink halo: the fused
-    kernel stores the slab-face populations straight into the neighbours' ghost planes.
+    The device side of a simulation: runtime handle, boundary lists on the device, kernel launches,
+    item properties, time stepping.  It is a mixin over an object that owns `domain`, `scheme`,
+    `container` (CudaContainer), `bc` (Boundary of this package), `kernels` (runtime.KernelLibrary),
+    `init_type` / `init_data` and the scalars t, nt, dt_, dim, extra_parameters -- i.e. what the
+    reference's constructor builds (pylbm/simulation.py:89-153).  Two front ends use it:
+    `pylbm_b200.Simulation` (this package's own dictionary front end, no pylbm needed) and
+    `pylbm_b200.plugin.CudaSimulation`, the class `pylbm.Simulation(dico)` instantiates for
+    generator='cuda' once `plugin.register()` ran (the reference's own constructor, unchanged).
     """
 
-    def __init__(self, dico, sorder=None, dtype="float64", check_inverse=False, initialize=True,
-                 slab=None, nccl_id=None, gather=None, compute_dtype=None):
-        generator = str(dico.get("generator", "cuda")).upper()
-        if generator != "CUDA":
-            raise ValueError(
-                "pylbm_b200 only provides generator='cuda' (got %r); there is no CPU fallback" % generator
-            )
-        rt.ensure_gpu()
+    @staticmethod
+    def _storage_names(dtype, compute_dtype):
+        names = {"float64": "f64", "f64": "f64", "float32": "f32", "f32": "f32"}
         try:
-            storage = {"float64": "f64", "f64": "f64", "float32": "f32", "f32": "f32"}[
-                dtype if isinstance(dtype, str) else str(np.dtype(dtype))]
+            storage = names[dtype if isinstance(dtype, str) else str(np.dtype(dtype))]
         except KeyError:
             raise ValueError("dtype must be float64 or float32 (storage of the populations), got %r" % (dtype,))
-        self.storage = storage
-        names = {"float64": "f64", "f64": "f64", "float32": "f32", "f32": "f32", None: "f64"}
         try:
-            compute = names[compute_dtype if isinstance(compute_dtype, (str, type(None))) else str(np.dtype(compute_dtype))]
+            compute = "f64" if compute_dtype is None else names[
+                compute_dtype if isinstance(compute_dtype, str) else str(np.dtype(compute_dtype))]
         except KeyError:
             raise ValueError("compute_dtype must be float64 or float32, got %r" % (compute_dtype,))
         if compute == "f32" and storage != "f32":
             raise ValueError("compute_dtype='float32' needs dtype='float32' (fp32 storage of the populations)")
-        self.compute = compute
+        return storage, compute
 
-        rank, nranks = slab if slab is not None else (0, 1)
-        topo = None
-        if nranks > 1:
-            from .stencil import Stencil
-
-            topo = SlabTopology(Stencil.extract_dim(dico), rank, nranks)
-            topo.gather = gather          # used by H5File to bring the slabs to rank 0
-        self.domain = Domain(dico, need_validation=False, topology=topo)
-        self.scheme = Scheme(dico, check_inverse=check_inverse, need_validation=False)
-        if self.domain.dim != self.scheme.dim:
-            raise ValueError("Solution: the dimension of the domain and of the scheme are not the same")
-
+    def _engine_defaults(self, storage, compute, slab=None, nccl_id=None, gather=None):
+        self.storage, self.compute = storage, compute
+        self.rank, self.nranks = slab if slab is not None else (0, 1)
+        self._nccl_id, self._gather = nccl_id, gather
         self._mc_version = -1
-        self._update_m = True
-        self.t = 0.0
-        self.nt = 0
-        self.dt_ = self.domain.dx / self.scheme.la
-        self.dim = self.domain.dim
-        self.extra_parameters = {}
-        self.rank, self.nranks = rank, nranks
-
-        # ---- generated kernels -----------------------------------------
-        user_algo = dico.get("lbm_algorithm", None) or {}
-        codegen_opt = dico.get("codegen_option", None)
-        want_source = bool(dico.get("show_code", False) or (codegen_opt and codegen_opt.get("directory")))
-        self.algo, lib_path, source = build_kernel_library(self.scheme, user_algo.get("settings", {}), storage,
-                                                           need_source=want_source, compute=compute)
-        if dico.get("show_code", False):
-            print(source)
-        if codegen_opt and codegen_opt.get("directory"):
-            outdir = os.path.realpath(codegen_opt["directory"])
-            os.makedirs(outdir, exist_ok=True)
-            with open(os.path.join(outdir, os.path.basename(lib_path)[3:-3] + ".cu"), "w") as fh:
-                fh.write(source)
-        self.kernels = rt.KernelLibrary(lib_path)
-        self.generator = types.SimpleNamespace(backend="CUDA", module=self.kernels)
-
-        # ---- storage ----------------------------------------------------
-        self.container = CudaContainer(self.domain, self.scheme, sorder, storage)
         self._handle = None
-
-        # ---- boundary lists ---------------------------------------------
-        self.bc = Boundary(self.domain, self.generator, dico)
-        for method in self.bc.methods:
-            method.set_iload()
-
-        self.init_type = dico.get("inittype", "moments")
-        self.init_data = dico.get("init", None)
-        self._nccl_id = nccl_id
-        self._gather = gather
-        self._need_init = True
-        if initialize:
-            self._initialize()
+        self._time_dependent = False
 
     # ------------------------------------------------------------------
     # `_update_m = True` means "F changed, the moments are stale" (reference: simulation.py:215-224);
@@ -267,8 +212,11 @@ class Simulation:
         desc.t_index = names.index("t") if "t" in names else -1
         try:
             values = self._scalar_values("one_time_step")
+            self._scalars_unresolved = False
         except KeyError:
-            values = [0.0] * len(names)   # user parameters may be given later (extra_parameters)
+            # user parameters may be given later (extra_parameters): resolved, loudly, by the first step
+            values = [0.0] * len(names)
+            self._scalars_unresolved = True
         for i, v in enumerate(values):
             desc.scalars[i] = v
         desc.t, desc.dt = self.t, self.dt
@@ -409,14 +357,21 @@ class Simulation:
         self.container.release_m()   # rebuilt on demand by f2m; frees nv * cells * 8 bytes of HBM
 
     # ---- whole-array kernels (reference: simulation.py:322-371) -------------
-    def _launch(self, name, src, dst, inner=False):
+    def _launch(self, name, src, dst, inner=False, kernels=None):
         grid = src.inner_grid() if inner else src.grid
         stream = rt.lib().lbm_sim_stream(self._handle) if self._handle else None
-        self.kernels.launch(name, src.ptr, dst.ptr, grid, self._scalar_values(name), stream)
+        (kernels or self.kernels).launch(name, src.ptr, dst.ptr, grid, self._scalar_values(name), stream)
         if self._handle:
             rt.check(rt.lib().lbm_sim_sync(self._handle), "sync")
         else:
             rt.check(rt.lib().lbm_device_sync(), "sync")
+
+    def _kernels_f64(self):
+        if self.storage == "f64":
+            return self.kernels
+        if self.__dict__.get("_kernels64") is None:
+            self._kernels64 = self._build_kernels("f64", "f64")
+        return self._kernels64
 
     def _scratch(self, nv, ncell, storage, slot):
         """cached 1-D device arrays for the small wall-value evaluations (time-dependent boundary
@@ -445,8 +400,10 @@ class Simulation:
     def m2f(self, m_user=None, f_user=None, **kwargs):
         if m_user is not None:
             dm = self._on_device(m_user)
-            df = self._scratch(dm.nv, dm.nspace[0], self.storage, 1)
-            self._launch("m2f", dm, df)
+            # wall equilibria stay fp64: with fp32 populations the m2f of the fp64-storage library of the
+            # same scheme is used (rhs = feq[k] -/+ feq[ksym] cancels, boundary.py:421-427)
+            df = self._scratch(dm.nv, dm.nspace[0], "f64", 1)
+            self._launch("m2f", dm, df, kernels=self._kernels_f64())
             f_user.array[...] = df.get().reshape(f_user.array.shape)
             return
         self._launch("m2f", self.container.m, self.container.F)
@@ -494,6 +451,11 @@ class Simulation:
             return self_.container.m[i]
 
         def put(self_, i, value):
+            # the moment array is rebuilt lazily (release_m): bring it up to date before one row is
+            # overwritten, so that the other rows keep the moments of the last f2m like the reference's
+            if self_.container._m is None or self_._update_m:
+                self_._update_m = False
+                self_.f2m()
             self_._update_m = False
             self_.container.m[i] = value
 
@@ -532,6 +494,7 @@ class Simulation:
 
     # ---- time stepping ------------------------------------------------------
     def _push_scalars(self):
+        self._scalars_unresolved = False
         names = self.kernels.scalars("one_time_step")
         if names and names != ["t"]:
             values = self._scalar_values("one_time_step")
@@ -559,7 +522,7 @@ class Simulation:
         self._update_m = True
         if self._time_dependent:
             self._update_time_bc()
-        if self.extra_parameters:
+        if self.extra_parameters or self._scalars_unresolved:
             self._push_scalars()
         rc = rt.lib().lbm_sim_step(self._handle, 1)
         if rc < 0:
@@ -579,7 +542,7 @@ class Simulation:
                 self.one_time_step()
             return
         self._update_m = True
-        if self.extra_parameters:
+        if self.extra_parameters or self._scalars_unresolved:
             self._push_scalars()
         rt.check(rt.lib().lbm_sim_use_graph(self._handle, 1 if graph else 0), "lbm_sim_use_graph")
         rt.check(rt.lib().lbm_sim_step(self._handle, int(nsteps)), "lbm_sim_step")
@@ -596,3 +559,87 @@ class Simulation:
 
     def __repr__(self):
         return "Simulation(generator='cuda', {}, {}, t={}, nt={})".format(self.domain, self.scheme, self.t, self.nt)
+
+
+class Simulation(CudaEngine):
+    """
+    Simulation(dico, sorder=None, dtype='float64', check_inverse=False, initialize=True,
+               slab=None, nccl_id=None, gather=None, compute_dtype=None)
+
+    `dico` is a pylbm dictionary (box, elements, space_step, scheme_velocity, schemes,
+    parameters, relative_velocity, init, inittype, boundary_conditions, generator,
+    codegen_option, lbm_algorithm, show_code).  `dtype='float32'` selects fp32 STORAGE of
+    the populations (arithmetic stays fp64) -- new functionality, the reference ignores
+    its dtype argument (simulation.py:89-91, storage.py:67).  `compute_dtype='float32'` (only with
+    dtype='float32') also runs the time-step kernels in fp32 arithmetic: the all-single-precision
+    mode, tolerance stated in tests/test_gpu_parity.py; moments (`sol.m`), initialisation and wall
+    equilibria are always computed in fp64.
+    `slab=(rank, nranks)` + `nccl_id` run this process as one x-slab of a multi-GPU run (NCCL
+    send/recv halo).  `gather(bytes) -> [bytes of every rank]` (an all-gather provided by the caller,
+    e.g. torch.distributed.all_gather_object) additionally enables the direct NVLink halo: the fused
+    kernel stores the slab-face populations straight into the neighbours' ghost planes.
+    """
+
+    def __init__(self, dico, sorder=None, dtype="float64", check_inverse=False, initialize=True,
+                 slab=None, nccl_id=None, gather=None, compute_dtype=None):
+        generator = str(dico.get("generator", "cuda")).upper()
+        if generator != "CUDA":
+            raise ValueError(
+                "pylbm_b200 only provides generator='cuda' (got %r); there is no CPU fallback" % generator
+            )
+        rt.ensure_gpu()
+        storage, compute = self._storage_names(dtype, compute_dtype)
+        self._engine_defaults(storage, compute, slab, nccl_id, gather)
+
+        rank, nranks = slab if slab is not None else (0, 1)
+        topo = None
+        if nranks > 1:
+            from .stencil import Stencil
+
+            topo = SlabTopology(Stencil.extract_dim(dico), rank, nranks)
+            topo.gather = gather          # used by H5File to bring the slabs to rank 0
+        self.domain = Domain(dico, need_validation=False, topology=topo)
+        self.scheme = Scheme(dico, check_inverse=check_inverse, need_validation=False)
+        if self.domain.dim != self.scheme.dim:
+            raise ValueError("Solution: the dimension of the domain and of the scheme are not the same")
+
+        self._update_m = True
+        self.t = 0.0
+        self.nt = 0
+        self.dt_ = self.domain.dx / self.scheme.la
+        self.dim = self.domain.dim
+        self.extra_parameters = {}
+
+        # ---- generated kernels -----------------------------------------
+        user_algo = dico.get("lbm_algorithm", None) or {}
+        codegen_opt = dico.get("codegen_option", None)
+        want_source = bool(dico.get("show_code", False) or (codegen_opt and codegen_opt.get("directory")))
+        self.algo, lib_path, source = build_kernel_library(self.scheme, user_algo.get("settings", {}), storage,
+                                                           need_source=want_source, compute=compute)
+        if dico.get("show_code", False):
+            print(source)
+        if codegen_opt and codegen_opt.get("directory"):
+            outdir = os.path.realpath(codegen_opt["directory"])
+            os.makedirs(outdir, exist_ok=True)
+            with open(os.path.join(outdir, os.path.basename(lib_path)[3:-3] + ".cu"), "w") as fh:
+                fh.write(source)
+        self.kernels = rt.KernelLibrary(lib_path)
+        self._algo_settings = user_algo.get("settings", {})
+        self.generator = types.SimpleNamespace(backend="CUDA", module=self.kernels)
+
+        # ---- storage ----------------------------------------------------
+        self.container = CudaContainer(self.domain, self.scheme, sorder, storage)
+
+        # ---- boundary lists ---------------------------------------------
+        self.bc = Boundary(self.domain, self.generator, dico)
+        for method in self.bc.methods:
+            method.set_iload()
+
+        self.init_type = dico.get("inittype", "moments")
+        self.init_data = dico.get("init", None)
+        self._need_init = True
+        if initialize:
+            self._initialize()
+
+    def _build_kernels(self, storage, compute):
+        return rt.KernelLibrary(build_kernel_library(self.scheme, self._algo_settings, storage, compute=compute)[1])

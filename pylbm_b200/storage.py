@@ -28,7 +28,7 @@ import sympy as sp
 
 from . import runtime as rt
 
-__all__ = ["DeviceArray", "HostArray"]
+__all__ = ["DeviceArray", "DeviceView", "HostArray"]
 
 
 def _roundup(n, m):
@@ -92,6 +92,29 @@ class Layout:
         return k * self.pstride + self.lead + (space[0] * n[1] + space[1]) * self.pitch + space[2]
 
 
+class DeviceView:
+    """what `Array.array` is for a device array (reference: storage.py:107-118 hands a NumPy or
+    pyopencl array to the generated functions): an opaque handle the CUDA module recognises."""
+
+    def __init__(self, dev):
+        self.dev = dev
+
+    def __getitem__(self, key):
+        return self
+
+    def __setitem__(self, key, other):      # Fnew.array[:] = F.array[:]  (simulation.py:320)
+        if isinstance(other, DeviceView):
+            self.dev.copy_from(other.dev)
+        else:
+            self.dev.set(np.asarray(other))
+
+    def copy(self):                          # fcopy = F.array.copy()  (boundary.py:549): the Bouzidi
+        return self                          # kernel gathers before it scatters, no snapshot needed
+
+    shape = property(lambda self: self.dev.shape)
+    size = property(lambda self: self.dev.size)
+
+
 class DeviceArray(_ConsmMixin):
     """
     Padded SoA array in HBM.  `nspace` includes the ghost layers (`vmax` per side).
@@ -153,6 +176,22 @@ class DeviceArray(_ConsmMixin):
             except Exception:
                 pass
             self.ptr = None
+
+    # ---- the rest of the reference's Array surface (storage.py:107-118, 306-367) ------------
+    array = property(lambda self: DeviceView(self))
+    swaparray = property(lambda self: self.get())
+    gpu_support = True
+
+    def generate(self, generator):
+        """the ghost-update kernels are part of the static runtime (k_periodic): nothing to generate
+        (reference: storage.py:370-420 generates update_x/y/z for its OpenCL backend)."""
+
+    def update(self):
+        """periodic ghost update of one rank, dimension by dimension (reference: storage.py:306-367)."""
+        vmax = (ctypes.c_int * 3)(*self.canonical_vmax)
+        mask = sum(1 << a for a in range(3) if self.canonical_vmax[a] > 0)
+        rt.check(rt.lib().lbm_periodic(self.ptr, ctypes.byref(self.grid), self.nv, self.storage_id, vmax, mask, None),
+                 "lbm_periodic")
 
     # ---- geometry helpers ------------------------------------------------
     def inner_grid(self):

@@ -13,6 +13,52 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def _gpu_available():
+    try:
+        from pylbm_b200 import runtime
+
+        return runtime.lib().lbm_device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    """tests marked `gpu` are skipped (not failed) on a box without a CUDA device or without nvcc."""
+    gpu_items = [item for item in items if "gpu" in item.keywords]
+    if not gpu_items or _gpu_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (or the runtime library cannot be built) on this box")
+    for item in gpu_items:
+        item.add_marker(skip)
+
+
+def reference_paths():
+    """sys.path entries that make the UNMODIFIED reference importable, or None: oracle/_ref (installed
+    by tools/make_ref.sh, travels to the GPU box with the working tree), else the read-only checkout of
+    the build container with the import shims of tools/refshim."""
+    installed = os.path.join(ROOT, "oracle", "_ref")
+    if os.path.isdir(os.path.join(installed, "pylbm")):
+        return [os.path.join(installed, "shims"), installed]
+    checkout = os.environ.get("PYLBM_REFERENCE", "/root/reference")
+    if os.path.isdir(os.path.join(checkout, "pylbm")):
+        return [os.path.join(ROOT, "tools", "refshim"), checkout]
+    return None
+
+
+@pytest.fixture(scope="session")
+def pylbm():
+    """the reference package (skips when it is not on this box)."""
+    paths = reference_paths()
+    if paths is None:
+        pytest.skip("reference pylbm not available on this box (run tools/make_ref.sh in the build container)")
+    for p in reversed(paths):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import pylbm as ref
+
+    return ref
+
+
 def case_id(name, kw):
     return name + "-" + "x".join(str(v) for v in kw.values())
 

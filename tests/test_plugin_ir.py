@@ -1,8 +1,8 @@
 """
 `generator='cuda'` registered inside the reference pylbm (pylbm_b200/plugin.py).
 
-Needs the reference importable (build container: /root/reference through tools/refshim); skipped
-elsewhere.  CPU only: the reference's own symbolic Routines are lowered to the per-cell IR, evaluated
+Needs the reference importable (oracle/_ref installed by tools/make_ref.sh, else /root/reference
+through tools/refshim: the `pylbm` fixture of conftest.py); skipped elsewhere.  CPU only: the reference's own symbolic Routines are lowered to the per-cell IR, evaluated
 with NumPy and compared with the literal C restatement; then `pylbm.Simulation(generator='cuda')` is
 driven up to its first device allocation.
 """
@@ -12,22 +12,6 @@ import sys
 
 import numpy as np
 import pytest
-
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-REFERENCE = os.environ.get("PYLBM_REFERENCE", "/root/reference")
-
-pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "pylbm")),
-                                reason="reference pylbm not available on this box")
-
-
-@pytest.fixture(scope="module")
-def pylbm():
-    for p in (REFERENCE, os.path.join(ROOT, "tools", "refshim")):
-        if p not in sys.path:
-            sys.path.insert(0, p)
-    import pylbm as ref
-
-    return ref
 
 
 def _routines(pylbm, dico):
@@ -115,6 +99,7 @@ def test_module_object_built_from_a_reference_simulation(pylbm):
     ref = pylbm.Simulation(cases.karman_d2q9(nx=32, ny=16, mod=pylbm, generator="cython"))
     routines = list(ref.generator.routines.values())
     module = CudaModule(routines)
+    assert module.lowering == "ir"
     for r in routines:
         fn = getattr(module, r.name)
         assert callable(fn) and isinstance(fn.arg_dict, dict)
