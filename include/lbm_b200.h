@@ -29,7 +29,18 @@
  * or -2000-x for argument errors); lbm_last_error() gives the message.  Nothing throws
  * or aborts.  The caller owns all buffers passed in; the runtime owns only what it
  * allocates itself (device copies of boundary lists, scratch, streams, events).
- * One host thread drives one GPU (one process per GPU); a context is not thread-safe.
+ * One host thread drives one GPU (one process per GPU); a context is not thread-safe (the staging
+ * buffers of lbm_array_h2d/d2h are process-wide and unsynchronised: one copy at a time per process).
+ *
+ * Limits (violations return an argument error, nothing is truncated silently):
+ *   populations per scheme          nv <= 64            (lbm_sim_desc.vel, lbmk_walls.rhs, PopSel)
+ *   runtime scalars of a kernel     nscalars <= 32      (lbm_sim_desc.scalars: t, dt, user symbols)
+ *   methods merged into one launch  <= 12               (lbm_sim_bc_groups; longer groups must be split
+ *                                                        by the caller, see boundary.merge_groups)
+ *   ghost width                     vmax[a] >= 0 per axis, n[a] >= 2*vmax[a] + 1
+ *   peer halo rendezvous            a neighbour that is more than PYLBM_B200_HALO_TIMEOUT_S seconds
+ *                                   late (default 30) makes the next lbm_sim_step / lbm_sim_sync /
+ *                                   lbm_sim_timer_stop return -2003 "peer halo timeout"
  */
 #ifndef LBM_B200_H
 #define LBM_B200_H

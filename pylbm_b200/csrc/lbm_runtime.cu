@@ -13,6 +13,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -49,7 +51,36 @@ extern "C" int lbm_device_count(void) {
     if (e != cudaSuccess) return set_error(-(int)e, "cudaGetDeviceCount", cudaGetErrorString(e));
     return n;
 }
-extern "C" int lbm_set_device(int device) { CUDA_TRY(cudaSetDevice(device)); return 0; }
+// Page-locked host buffers (lbm_host_alloc, the staging side of lbm_array_h2d/d2h) should live on the
+// NUMA node the GPU hangs off: with one process per GPU on a two-socket host, half of the ranks
+// otherwise DMA across the socket interconnect.  Sets the calling thread's memory policy to "prefer
+// the GPU's node" (threads created later inherit it); CPU affinity is left alone.  Best effort:
+// any failure leaves the default policy.  PYLBM_B200_NO_NUMA=1 disables it.
+static void prefer_gpu_numa_node(int device) {
+    if (getenv("PYLBM_B200_NO_NUMA")) return;
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* fh = fopen(path, "r");
+    if (!fh) return;
+    int node = -1;
+    if (fscanf(fh, "%d", &node) != 1) node = -1;
+    fclose(fh);
+    if (node < 0 || node >= 1024) return;
+    unsigned long mask[1024 / (8 * sizeof(unsigned long))];
+    memset(mask, 0, sizeof(mask));
+    mask[node / (8 * sizeof(unsigned long))] |= 1UL << (node % (8 * sizeof(unsigned long)));
+    const int MPOL_PREFERRED_ = 1;
+    syscall(SYS_set_mempolicy, MPOL_PREFERRED_, mask, (unsigned long)(1024 + 1));
+}
+
+extern "C" int lbm_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    prefer_gpu_numa_node(device);
+    return 0;
+}
 extern "C" int lbm_device_sync(void) { CUDA_TRY(cudaDeviceSynchronize()); return 0; }
 extern "C" int lbm_mem_info(uint64_t* free_bytes, uint64_t* total_bytes) {
     size_t f = 0, t = 0;
@@ -114,6 +145,7 @@ struct RepackPipe {
     int device = -1;
     double* stage[2] = {nullptr, nullptr};
     cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
     long long chunk = 0;   // elements per staging buffer
 };
 static RepackPipe g_pipe;
@@ -129,6 +161,7 @@ static int repack_pipe(long long want) {
         g_pipe.st[b] = nullptr;
     }
     g_pipe.device = -1;
+    if (!g_pipe.ready) CUDA_TRY(cudaEventCreateWithFlags(&g_pipe.ready, cudaEventDisableTiming));
     for (int b = 0; b < 2; ++b) {
         CUDA_TRY(cudaMalloc(&g_pipe.stage[b], (size_t)want * 8));
         CUDA_TRY(cudaStreamCreateWithFlags(&g_pipe.st[b], cudaStreamNonBlocking));
@@ -147,7 +180,10 @@ static int repack(void* dev, double* host, const lbmk_grid* g, int storage, int 
     const long long chunk = total < (8LL << 20) ? total : (8LL << 20);     // 64 MB of doubles per buffer
     int rc = repack_pipe(chunk);
     if (rc) return rc;
-    CUDA_TRY(cudaDeviceSynchronize());        // everything enqueued so far (any stream) has finished
+    // everything enqueued so far on the blocking streams (the simulations' streams) precedes the legacy
+    // default stream; the two copy streams wait for that point on the device, the host does not stall
+    CUDA_TRY(cudaEventRecord(g_pipe.ready, 0));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaStreamWaitEvent(g_pipe.st[i], g_pipe.ready, 0));
     cudaError_t e = cudaSuccess;
     int b = 0;
     for (long long first = 0; first < total && e == cudaSuccess; first += chunk, b ^= 1) {
@@ -483,13 +519,34 @@ __global__ void k_signal(unsigned long long* to_left, unsigned long long* to_rig
     if (threadIdx.x == 1) atomicAdd_system(to_right, 1ULL);   // and the LEFT neighbour of my right rank
 }
 
-__global__ void k_wait(unsigned long long* flags) {
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// `err` is a word of page-locked host memory mapped into the device: a neighbour that does not arrive
+// within `timeout_ns` (a dead or hung rank) makes the wait give up, record which side was late
+// (bit 0: left, bit 1: right) and return, so that the step sequence drains instead of spinning for
+// ever; the host reports it at the next lbm_sim_sync / lbm_sim_timer_stop / lbm_sim_step.  Once the
+// word is set every later wait returns at once (the results are void from the first miss on).
+__global__ void k_wait(unsigned long long* flags, volatile unsigned int* err, unsigned long long timeout_ns) {
     // flags[0], flags[1]: arrivals from the left / right neighbour; flags[2], flags[3]: my epochs
     const int i = threadIdx.x;
     if (i < 2) {
         const unsigned long long want = flags[2 + i] + 1ULL;
         volatile unsigned long long* arr = flags + i;
-        while (*arr < want) { __nanosleep(100); }
+        if (*arr < want && *err == 0u) {
+            const unsigned long long t0 = global_ns();
+            unsigned int spins = 0;
+            while (*arr < want) {
+                __nanosleep(100);
+                if ((++spins & 1023u) == 0u && global_ns() - t0 > timeout_ns) {
+                    atomicOr_system((unsigned int*)err, 1u << i);
+                    break;
+                }
+            }
+        }
         flags[2 + i] = want;
     }
     __threadfence_system();
@@ -536,6 +593,9 @@ struct lbm_sim {
     int peer_nin_lo = 0;
     unsigned long long* flags = nullptr;          // [0],[1]: arrivals from left/right; [2],[3]: my epochs
     unsigned long long* peer_flags[2] = {nullptr, nullptr};
+    unsigned int* wait_err = nullptr;             // page-locked, mapped: set by k_wait on a timeout
+    unsigned int* wait_err_dev = nullptr;         // device alias of wait_err
+    unsigned long long wait_timeout_ns = 30ULL * 1000000000ULL;
     // CUDA graph of two consecutive steps (f->fnew, fnew->f)
     int use_graph = 0;
     cudaGraphExec_t graph = nullptr;
@@ -603,6 +663,19 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
     return s;
 }
 
+// a neighbour rank missed a halo rendezvous (k_wait timed out): every result since then is void
+static int check_peers(lbm_sim* s) {
+    if (s->wait_err && *(volatile unsigned int*)s->wait_err) {
+        char msg[160];
+        const unsigned int e = *(volatile unsigned int*)s->wait_err;
+        snprintf(msg, sizeof(msg), "rank %d waited more than %.0f s for its %s%s%s neighbour (dead or hung rank?)",
+                 s->rank, (double)s->wait_timeout_ns * 1e-9, (e & 1u) ? "left" : "", (e == 3u) ? " and " : "",
+                 (e & 2u) ? "right" : "");
+        return set_error(-2003, "peer halo timeout", msg);
+    }
+    return 0;
+}
+
 static void free_bc(BcMethod& b) {
     cudaFree(b.istore); cudaFree(b.iload0); cudaFree(b.iload1); cudaFree(b.rhs); cudaFree(b.dist);
 }
@@ -620,6 +693,7 @@ extern "C" void lbm_sim_destroy(lbm_sim* s) {
         }
     }
     cudaFree(s->flags);
+    if (s->wait_err) cudaFreeHost(s->wait_err);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     for (auto& b : s->bcs) free_bc(b);
     cudaFree(s->scratch);
@@ -714,6 +788,10 @@ extern "C" int lbm_sim_bc_stale_only(lbm_sim* s, int ibc, int flag) {
 extern "C" int lbm_sim_set_walls(lbm_sim* s, lbmk_launch_walls_fn launcher, const lbmk_walls* walls) {
     if (!s) return ARG_ERROR("null sim");
     if (walls && !launcher) return ARG_ERROR("lbm_sim_set_walls: launcher missing");
+    if (walls && !(s->wrap_mask & (1 << 2)))
+        // the z periodic copy would run on fresh ghosts and overwrite the wall values the kernel stored
+        return ARG_ERROR("lbm_sim_set_walls: the fused kernel does not maintain the ghosts of the fastest axis "
+                         "(PYLBM_B200_NO_WRAP / NO_ZWRAP, or the axis is too short)");
     if (walls) {
         s->walls = *walls;
         s->walls_fn = launcher;
@@ -872,7 +950,7 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
             // fused kernel: just wait for both of them to have finished it (once per array state:
             // lbm_sim_boundary_condition may already have done it)
             if (!s->waited) {
-                k_wait<<<1, 32, 0, st>>>(s->flags);
+                k_wait<<<1, 32, 0, st>>>(s->flags, s->wait_err_dev, s->wait_timeout_ns);
                 s->launches += 1;
                 s->waits += 1;
                 s->waited = 1;
@@ -883,7 +961,7 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
             if (s->peers_ready && s->waits < s->signals) {
                 // a signal of the previous step is still pending (the ghosts were invalidated from
                 // outside): consume it so that the arrival counters stay in step
-                k_wait<<<1, 32, 0, st>>>(s->flags);
+                k_wait<<<1, 32, 0, st>>>(s->flags, s->wait_err_dev, s->wait_timeout_ns);
                 s->launches += 1;
                 s->waits += 1;
             }
@@ -974,6 +1052,7 @@ static int build_graph(lbm_sim* s) {
 
 extern "C" int lbm_sim_step(lbm_sim* s, int nsteps) {
     if (!s || nsteps < 0) return ARG_ERROR("lbm_sim_step");
+    if (int rc = check_peers(s)) return rc;
     int done = 0;
     const bool graph_ok = s->use_graph && s->d.t_index < 0 && (s->nranks == 1 || s->peers_ready) && !s->profile;
     while (done < nsteps) {
@@ -1014,7 +1093,7 @@ extern "C" int lbm_sim_sync(lbm_sim* s) {
     if (!s) return ARG_ERROR("null sim");
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->comm_stream));
-    return 0;
+    return check_peers(s);
 }
 
 extern "C" int lbm_sim_state(lbm_sim* s, void** f, void** fnew, double* t, int64_t* nt) {
@@ -1058,7 +1137,7 @@ extern "C" int lbm_sim_timer_stop(lbm_sim* s, float* ms) {
     CUDA_TRY(cudaEventRecord(s->ev_stop, s->stream));
     CUDA_TRY(cudaEventSynchronize(s->ev_stop));
     CUDA_TRY(cudaEventElapsedTime(ms, s->ev_start, s->ev_stop));
-    return 0;
+    return check_peers(s);
 }
 
 extern "C" int lbm_sim_profile(lbm_sim* s, int enable) {
@@ -1100,6 +1179,11 @@ extern "C" int lbm_sim_ipc_export(lbm_sim* s, void* blob256) {
     if (!s->flags) {
         CUDA_TRY(cudaMalloc(&s->flags, 4 * sizeof(unsigned long long)));
         CUDA_TRY(cudaMemset(s->flags, 0, 4 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaHostAlloc((void**)&s->wait_err, sizeof(unsigned int), cudaHostAllocMapped));
+        *s->wait_err = 0u;
+        CUDA_TRY(cudaHostGetDevicePointer((void**)&s->wait_err_dev, s->wait_err, 0));
+        const char* env = getenv("PYLBM_B200_HALO_TIMEOUT_S");
+        if (env && atof(env) > 0.0) s->wait_timeout_ns = (unsigned long long)(atof(env) * 1e9);
         CUDA_TRY(cudaDeviceSynchronize());
     }
     IpcBlob b;

@@ -421,9 +421,17 @@ class CudaEngine:
         self._launch("relaxation", self.container.m, self.container.m)
 
     def source_term(self, fraction_of_time_step=1.0, **kwargs):
+        """half a time step of explicit Euler on the moments (ode.py:11-16: `m + dt/2 * rhs`), whatever
+        `fraction_of_time_step` says -- the reference does not forward that argument to its kernel
+        either (simulation.py:340-345)."""
+        if "source_term" not in self.kernels.routines:
+            raise KeyError("source_term: the scheme has no source term")
         self._launch("source_term", self.container.m, self.container.m, inner=True)
 
     def transport(self, **kwargs):
+        """Fnew <- streamed F, then F <- Fnew: the result is left in F ("the array _F is modified",
+        simulation.py:322-327, and what the reference's NumPy backend does; its Cython backend leaves
+        the result in Fnew, base.py:289-296)."""
         F, Fnew = self.container.F, self.container.Fnew
         self._launch("transport", F, Fnew, inner=True)
         F.copy_from(Fnew)

@@ -265,6 +265,9 @@ class DeviceArray(_ConsmMixin):
             host = np.empty(self.nspace)
             host[...] = values
             self.set(host, int(key))
+        elif (key is Ellipsis or (isinstance(key, slice) and key == slice(None))) \
+                and getattr(values, "shape", None) == self.shape:
+            self.set(values)                     # whole array: no read-modify-write
         else:
             host = self.get()
             host[key] = values

@@ -1,5 +1,6 @@
-"""bench.py contract on the CPU: the reference arm (`--impl reference`: the oracle's OpenMP restatement of
-the reference's Cython path on the host cores) prints ONE JSON line with the keys the driver reads."""
+"""bench.py contract on the CPU: the reference arm (`--impl reference`: the unmodified reference's own
+Cython generator from oracle/_ref on one host core, the oracle's OpenMP restatement when the reference is
+not installed) prints ONE JSON line with the keys the driver reads."""
 import json
 import os
 import subprocess
@@ -20,7 +21,15 @@ def test_reference_arm_prints_one_json_line():
     assert line["impl"] == "reference" and line["metric"] == "MLUPS" and line["unit"] == "MLUPS"
     assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["value"] > 0
     assert line["steps"] == 2 and line["warmup"] == 3 and line["n_gpus"] == 1
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    installed = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "pylbm"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if installed else "port")
+    assert line["cpu_baseline"]["cores"] >= 1
+    if installed:
+        assert line["cpu_baseline"]["cores"] == 1 and "generator='cython'" in line["cpu_baseline"]["sample"]
+        assert line["cpu_port"]["kind"] == "port"
+    # the same `config` keys as the device arm prints (the driver compares the two dictionaries)
+    assert set(line["config"]) == {"workload", "case", "n", "storage", "arithmetic", "l2"}
+    assert set(line["run"]) == {"api", "parallelism", "halo", "setup_s"}
     assert line["cpu_baseline"]["value"] == line["value"] and "sample" in line["cpu_baseline"]
     assert line["e2e"] == {"value": line["value"], "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]

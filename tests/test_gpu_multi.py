@@ -166,3 +166,132 @@ def test_reference_demos_on_slabs(test, halo, tmp_path):
         for key in expected["ref"]:
             whole = np.concatenate([results[r][key] for r in range(world)], axis=0)
             assert np.array_equal(back[key], whole.T)
+
+
+def _timeout_worker(rank, world, nccl_id, queue, shared, barrier):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    os.environ["PYLBM_B200_HALO_TIMEOUT_S"] = "2"
+    import pylbm_b200
+    from pylbm_b200 import cases, runtime as rt
+
+    rt.check(rt.lib().lbm_set_device(rank), "lbm_set_device")
+
+    def gather(blob):
+        shared[rank] = blob
+        barrier.wait()
+        return [shared[r] for r in range(world)]
+
+    sim = pylbm_b200.Simulation(cases.karman_d2q9(nx=64, ny=32), slab=(rank, world), nccl_id=nccl_id, gather=gather)
+    sim.run(4)
+    sim.synchronize()
+    barrier.wait()
+    message = ""
+    if rank == 0:
+        # rank 1 stops stepping (a dead rank): my next steps wait for a signal that never comes
+        try:
+            sim.run(3)
+            sim.synchronize()
+        except rt.LbmError as exc:
+            message = str(exc)
+    barrier.wait()
+    queue.put((rank, message))
+
+
+def test_a_silent_neighbour_is_reported_not_waited_for_ever():
+    """k_wait gives up after PYLBM_B200_HALO_TIMEOUT_S seconds and the next runtime call says which
+    neighbour was late (the default is 30 s); without it one dead rank hangs the node silently."""
+    import ctypes
+    import multiprocessing as mp
+
+    from pylbm_b200 import runtime as rt
+
+    if rt.lib().lbm_device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2
+    raw = (ctypes.c_char * 128)()
+    rt.check(rt.lib().lbm_comm_unique_id(raw), "lbm_comm_unique_id")
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    manager = ctx.Manager()
+    shared, barrier = manager.dict(), manager.Barrier(world)
+    procs = [ctx.Process(target=_timeout_worker, args=(r, world, bytes(raw.raw), queue, shared, barrier))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+    assert "peer halo timeout" in results[0] and "neighbour" in results[0], results[0]
+
+
+def _plugin_worker(rank, world, nccl_id, case, kw, nsteps, queue, shared, barrier):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    from conftest import reference_paths
+
+    for p in reversed(reference_paths()):
+        sys.path.insert(0, p)
+    import pylbm
+    from pylbm_b200 import cases, plugin, runtime as rt
+
+    rt.check(rt.lib().lbm_set_device(rank), "lbm_set_device")
+
+    def gather(blob):
+        shared[rank] = blob
+        barrier.wait()
+        out = [shared[r] for r in range(world)]
+        barrier.wait()
+        return out
+
+    plugin.register()
+    plugin.configure(slab=(rank, world), nccl_id=nccl_id, gather=gather)
+    sol = pylbm.Simulation(cases.CASES[case](perturb=cases.WAVE, mod=pylbm, generator="cuda", **kw))
+    for _ in range(nsteps):
+        sol.one_time_step()
+    out = {str(k): sol.m[k].copy() for k in sol.scheme.consm}
+    sol.synchronize()
+    queue.put((rank, out))
+
+
+@pytest.mark.parametrize("case,kw", [("karman_d2q9", dict(nx=128, ny=32)), ("lid_cavity_d3q19", dict(n=16))])
+def test_pylbm_simulation_on_slabs(case, kw):
+    """the north-star interface, one process per GPU: `pylbm.Simulation(dico, generator='cuda')` cut into
+    x-slabs (fused NVLink halo) reproduces the single-GPU run of the same interface."""
+    import ctypes
+    import multiprocessing as mp
+
+    from conftest import reference_paths
+
+    if reference_paths() is None:
+        pytest.skip("reference pylbm not installed (tools/make_ref.sh)")
+    for p in reversed(reference_paths()):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import pylbm
+    from pylbm_b200 import cases, plugin, runtime as rt
+
+    if rt.lib().lbm_device_count() < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world, nsteps = 2, 20
+    raw = (ctypes.c_char * 128)()
+    rt.check(rt.lib().lbm_comm_unique_id(raw), "lbm_comm_unique_id")
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    manager = ctx.Manager()
+    shared, barrier = manager.dict(), manager.Barrier(world)
+    procs = [ctx.Process(target=_plugin_worker, args=(r, world, bytes(raw.raw), case, kw, nsteps, queue, shared, barrier))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    plugin.register()
+    ref = pylbm.Simulation(cases.CASES[case](perturb=cases.WAVE, mod=pylbm, generator="cuda", **kw))
+    for _ in range(nsteps):
+        ref.one_time_step()
+    fluid = ref.domain.in_or_out[tuple(slice(v, -v) for v in ref.domain.stencil.vmax)] == ref.domain.valin
+    for key in ref.scheme.consm:
+        whole = np.concatenate([results[r][str(key)] for r in range(world)], axis=0)
+        full = ref.m[key]
+        assert np.abs(whole[fluid] - full[fluid]).max() <= 1e-12 * np.abs(full[fluid]).max()
