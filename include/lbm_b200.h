@@ -147,6 +147,17 @@ int lbm_sim_bc_stale_only(lbm_sim* sim, int ibc, int flag);
 /* Let the fused kernel apply the bounce-back walls of the fastest axis (lbmk_walls, lbmk.h);
  * `launcher` = lbmk_one_time_step_walls of the kernel library.  walls = NULL switches it off. */
 int lbm_sim_set_walls(lbm_sim* sim, lbmk_launch_walls_fn launcher, const lbmk_walls* walls);
+/* Let the fused kernel evaluate the boundary entries itself (lbmk_tasks, lbmk.h): a time step is then
+ * ONE kernel launch.  `launcher` = lbmk_one_time_step_tasks of the kernel library.  HOST arrays, one
+ * entry per task, sorted by block: code / l0 / l1 / dist as in lbmk_tasks; ibc[t] and entry[t] name
+ * the registered method (lbm_sim_add_bc index) and the position inside its lists whose right-hand
+ * side the task uses (so lbm_sim_set_rhs keeps working).  The registered methods stay: they are what
+ * lbm_sim_boundary_condition applies.  ntasks < 0 switches the table off.  Not combined with
+ * lbm_sim_set_walls. */
+int lbm_sim_set_tasks(lbm_sim* sim, lbmk_launch_tasks_fn launcher, int64_t ntasks, int64_t nblocks,
+                      const int32_t* block_ptr, const uint32_t* code, const int64_t* l0, const int64_t* l1,
+                      const double* dist, const int32_t* ibc, const int64_t* entry,
+                      int ngroups_y, int ngroups_x, int tx);
 /* Merged launches: the registered methods [group_ptr[g], group_ptr[g+1]) run as ONE kernel launch.
  * The caller must have proved that, inside a group, no entry reads or overwrites a position that an
  * entry of ANOTHER method of the group stores (results are then bit-identical to running the methods

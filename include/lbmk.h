@@ -81,6 +81,29 @@ typedef struct {
     double rhs[64];    /* per LOADED population k (the one moving towards the wall)       */
 } lbmk_walls;
 
+/*
+ * Boundary entries evaluated inside the fused kernel ("tasks").  The entry `f_k(c_out) = value` of a
+ * boundary method (reference loops: boundary.py:462-464, 608-618, 678-680, 745-756, 818) is read by
+ * exactly one pull of the following fused kernel: cell c_out + v_k, population k.  With a task table the
+ * 128-thread block that owns the pulling cell evaluates its entries itself -- one entry per thread, the
+ * arithmetic of the list kernel (lbm_bc_apply), values handed over through shared memory -- so a time
+ * step is ONE launch and the scattered ghost stores / re-loads disappear.  The caller
+ * (boundary.plan_tasks) proves that no entry reads a position another entry stores; then the input
+ * array alone determines every value and the result is bit-identical to list kernels + pull.
+ * All pointers are DEVICE pointers; tasks are sorted by block: block b (linear index
+ * ((i0 - w[0]) * ngroups_y + row group) * ngroups_x + chunk of the fastest axis) owns
+ * [block_ptr[b], block_ptr[b+1]).
+ */
+typedef struct {
+    const int* block_ptr;          /* [nblocks + 1]                                               */
+    const unsigned* code;          /* thread in block | population k << 8 | LBM_BC_* kind << 16    */
+    const long long* l0;           /* element positions read in the INPUT array (lbmk_grid layout) */
+    const long long* l1;           /* second load of the Bouzidi kinds                             */
+    const double* const* rhs;      /* address of the entry's right-hand side (NULL: Neumann)       */
+    const double* dist;            /* Bouzidi coefficient                                          */
+    int ngroups_y, ngroups_x, tx;  /* launch geometry the table was built for (checked)            */
+} lbmk_tasks;
+
 /* ABI version the library was generated for. */
 int lbmk_abi_version(void);
 
@@ -110,6 +133,12 @@ typedef int (*lbmk_launch_walls_fn)(const void* fin, void* fout, const lbmk_grid
                                     const lbmk_peers* peers, const lbmk_walls* walls, void* stream);
 int lbmk_one_time_step_walls(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
                              const lbmk_peers* peers, const lbmk_walls* walls, void* stream);
+/* same with the boundary entries of the step evaluated by the kernel (tasks may be NULL);
+ * returns -4 when the table does not match the launch geometry */
+typedef int (*lbmk_launch_tasks_fn)(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                                    const lbmk_peers* peers, const lbmk_tasks* tasks, void* stream);
+int lbmk_one_time_step_tasks(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                             const lbmk_peers* peers, const lbmk_tasks* tasks, void* stream);
 int lbmk_transport(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_f2m(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 /* conserved moments only: fout has nconsm populations (rows 0..nconsm-1 of M f), same grid */

@@ -30,7 +30,7 @@ from .storage import HostArray
 
 __all__ = [
     "Boundary", "BoundaryMethod", "BounceBack", "BouzidiBounceBack", "AntiBounceBack",
-    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule", "merge_groups", "plan_walls",
+    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule", "merge_groups", "plan_walls", "plan_tasks",
 ]
 
 
@@ -205,6 +205,118 @@ def plan_walls(methods, array, velocities, symmetric):
             if ((c2 < w[2]) | (c2 >= n[2] - w[2])).any():
                 return None
     return walls, masks
+
+
+def plan_tasks(methods, array, velocities):
+    """
+    Task table for the fused kernel (include/lbmk.h: lbmk_tasks): every boundary entry is evaluated by the
+    128-thread block that owns the cell pulling its value, instead of by a list kernel.
+
+    methods    [{"kind", "store", "loads": [positions, ...], "dist" (or None), "single": bool}] in
+               application order (device positions of `array`, device order of the entries)
+    array      layout of the populations (storage.Layout / DeviceArray), with `tx` threads of a block
+               along the fastest axis
+    velocities integer lattice velocities [Q, dim]
+
+    The reference applies the methods one after the other on F, then pulls (simulation.py:373-420).  An
+    entry stores population k of an outside cell c_out, which exactly one pull reads: cell c_out + v_k.
+    Evaluating the entries from the INPUT array at pull time gives the same populations iff
+      * every method is one gather-free level (boundary.schedule), and
+      * no entry -- of any method -- reads a position that an entry stores (then every value only
+        depends on populations the previous fused launch wrote), except a Neumann entry copying a
+        position stored EARLIER in the sequence (the edge entries of an outlet next to a wall): it
+        inherits the definition of the entry it copies;
+    of several entries storing the same position the last one in application order wins, and an entry
+    whose value no interior cell pulls is dropped.  Returns None when the conditions do not hold, else
+    a dict of arrays sorted by block.
+    """
+    dim = array.dim
+    n = array.canonical_n
+    w = array.canonical_vmax
+    if len(velocities) > 64 or any(not m["single"] for m in methods):
+        return None
+    sizes = [len(m["store"]) for m in methods]
+    if sum(sizes) == 0 or sum(sizes) >= 2 ** 31:
+        return None
+    store = np.concatenate([np.asarray(m["store"], dtype=np.int64) for m in methods])
+    ibc = np.concatenate([np.full(sz, i, dtype=np.int32) for i, sz in enumerate(sizes)])
+    entry = np.concatenate([np.arange(sz, dtype=np.int64) for sz in sizes])
+    kind = np.concatenate([np.full(sz, m["kind"], dtype=np.int64) for m, sz in zip(methods, sizes)])
+    l0 = np.concatenate([np.asarray(m["loads"][0], dtype=np.int64) for m in methods])
+    l1 = np.concatenate([np.asarray(m["loads"][1], dtype=np.int64) if len(m["loads"]) > 1
+                         else np.zeros(sz, dtype=np.int64) for m, sz in zip(methods, sizes)])
+    dist = np.concatenate([np.asarray(m["dist"], dtype=np.float64) if m.get("dist") is not None
+                           else np.zeros(sz) for m, sz in zip(methods, sizes)])
+    two = (kind == rt.BC_BOUZIDI_BOUNCE_BACK) | (kind == rt.BC_BOUZIDI_ANTI_BOUNCE_BACK)
+    # positions stored, with their LAST writer in application order (global entry index)
+    upos, last_rev = np.unique(store[::-1], return_index=True)
+    last_writer = store.size - 1 - last_rev
+
+    def reads_a_store(idx):
+        hit = _member(upos, l0[idx])
+        hit |= two[idx] & _member(upos, l1[idx])
+        return hit
+
+    chained = reads_a_store(np.arange(store.size))
+    # A Neumann entry copying a position that an EARLIER entry stored (an outlet next to a wall) pulls
+    # what that entry computes: it inherits its definition.  Anything else that reads a stored position
+    # (an interpolation through a stored value, a position stored LATER in the sequence, a Bouzidi
+    # snapshot) keeps the list kernels.
+    pending = np.nonzero(chained)[0]
+    while pending.size:
+        if (kind[pending] != rt.BC_NEUMANN).any():
+            return None
+        writer = last_writer[np.searchsorted(upos, l0[pending])]
+        if (writer >= pending).any():
+            return None
+        ready = ~chained[writer]
+        if not ready.any():
+            return None
+        dst, src = pending[ready], writer[ready]
+        for arr in (kind, l0, l1, dist, ibc, entry, two):
+            arr[dst] = arr[src]
+        chained[dst] = False
+        pending = pending[~ready]
+    # last writer of every position
+    _, last = np.unique(store[::-1], return_index=True)
+    keep = np.sort(store.size - 1 - last)
+    # the cell that pulls (k, c_out) is c_out + v_k
+    pstride, pitch, lead = array.pstride, array.pitch, array.lead
+    pos = store[keep]
+    k = pos // pstride
+    r = pos - k * pstride - lead
+    row = r // pitch
+    c = [row // n[1], row % n[1], r - row * pitch]
+    vel = np.zeros((len(velocities), 3), dtype=np.int64)
+    vel[:, 3 - dim:] = np.asarray(velocities, dtype=np.int64)[:, :dim]
+    c = [c[a] + vel[k, a] for a in range(3)]
+    inside = np.ones(pos.size, dtype=bool)
+    for a in range(3):
+        inside &= (c[a] >= w[a]) & (c[a] < n[a] - w[a])
+    keep, k = keep[inside], k[inside]
+    c = [ca[inside] for ca in c]
+    tx = int(array.tx)
+    ty = 128 // tx
+    ngx = -(-(n[2] - 2 * w[2]) // tx)
+    ngy = -(-(n[1] - 2 * w[1]) // ty)
+    r2, r1 = c[2] - w[2], c[1] - w[1]
+    block = ((c[0] - w[0]) * ngy + r1 // ty) * ngx + r2 // tx
+    thread = (r1 % ty) * tx + r2 % tx
+    nblocks = int((n[0] - 2 * w[0]) * ngy * ngx)
+    if nblocks + 1 >= 2 ** 31:
+        return None
+    order = np.argsort(block, kind="stable")
+    keep, k, block, thread = keep[order], k[order], block[order], thread[order]
+    block_ptr = np.zeros(nblocks + 1, dtype=np.int32)
+    np.cumsum(np.bincount(block, minlength=nblocks), out=block_ptr[1:])
+    code = (thread | (k << 8) | (kind[keep] << 16)).astype(np.uint32)
+    return {
+        "ntasks": int(keep.size), "nblocks": nblocks, "block_ptr": block_ptr, "code": code,
+        "l0": np.ascontiguousarray(l0[keep]), "l1": np.ascontiguousarray(l1[keep]),
+        "dist": np.ascontiguousarray(dist[keep]), "ibc": np.ascontiguousarray(ibc[keep]),
+        "entry": np.ascontiguousarray(entry[keep]), "ngroups_y": int(ngy), "ngroups_x": int(ngx), "tx": tx,
+        "nentries": int(store.size),
+    }
 
 
 def schedule(store, loads, snapshot=False):

@@ -574,6 +574,8 @@ struct lbm_sim {
     std::vector<int> bc_groups;                   // first method of each merged launch (+ end); empty: none
     lbmk_launch_walls_fn walls_fn = nullptr;      // fused kernel applies the walls of the fastest axis
     lbmk_walls walls;
+    lbmk_launch_tasks_fn tasks_fn = nullptr;      // fused kernel evaluates the boundary entries itself
+    lbmk_tasks tasks;                             // device arrays owned by this object
     double* scratch = nullptr;
     long long scratch_n = 0;
     cudaStream_t stream = nullptr, comm_stream = nullptr;
@@ -584,6 +586,9 @@ struct lbm_sim {
     int rank = 0, nranks = 1;
     int slab_axis = 0;
     // direct NVLink halo (CUDA IPC): peer arrays [side lo/hi][buffer A/B], arrival counters
+    int xchg_inflight = 0;                        // NCCL halo: the exchange for the CURRENT f was issued on
+                                                  // comm_stream during the previous step (ev_comm marks its end)
+    int overlap = 1;                              // NCCL halo: exchange of step s+1 || inner cells of step s
     int peers_ready = 0;
     long long signals = 0, waits = 0;             // enqueued so far (host-side bookkeeping)
     int waited = 0;                               // the wait for the current f was already enqueued
@@ -680,6 +685,14 @@ static void free_bc(BcMethod& b) {
     cudaFree(b.istore); cudaFree(b.iload0); cudaFree(b.iload1); cudaFree(b.rhs); cudaFree(b.dist);
 }
 
+static void free_tasks(lbm_sim* s) {
+    if (!s->tasks_fn) return;
+    cudaFree((void*)s->tasks.block_ptr); cudaFree((void*)s->tasks.code); cudaFree((void*)s->tasks.l0);
+    cudaFree((void*)s->tasks.l1); cudaFree((void*)s->tasks.rhs); cudaFree((void*)s->tasks.dist);
+    memset(&s->tasks, 0, sizeof(s->tasks));
+    s->tasks_fn = nullptr;
+}
+
 extern "C" void lbm_sim_destroy(lbm_sim* s) {
     if (!s) return;
     cudaStreamSynchronize(s->stream);
@@ -695,6 +708,7 @@ extern "C" void lbm_sim_destroy(lbm_sim* s) {
     cudaFree(s->flags);
     if (s->wait_err) cudaFreeHost(s->wait_err);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    free_tasks(s);
     for (auto& b : s->bcs) free_bc(b);
     cudaFree(s->scratch);
     for (auto e : s->prof_events) cudaEventDestroy(e);
@@ -774,6 +788,7 @@ extern "C" int lbm_sim_add_bc(lbm_sim* s, int kind, int64_t ncond, const int64_t
     }
     s->bcs.push_back(b);
     s->bc_groups.clear();
+    free_tasks(s);               // a task table describes ALL registered entries
     drop_graph(s);
     return (int)s->bcs.size() - 1;
 }
@@ -788,6 +803,7 @@ extern "C" int lbm_sim_bc_stale_only(lbm_sim* s, int ibc, int flag) {
 extern "C" int lbm_sim_set_walls(lbm_sim* s, lbmk_launch_walls_fn launcher, const lbmk_walls* walls) {
     if (!s) return ARG_ERROR("null sim");
     if (walls && !launcher) return ARG_ERROR("lbm_sim_set_walls: launcher missing");
+    if (walls && s->tasks_fn) return ARG_ERROR("lbm_sim_set_walls: not combined with lbm_sim_set_tasks");
     if (walls && !(s->wrap_mask & (1 << 2)))
         // the z periodic copy would run on fresh ghosts and overwrite the wall values the kernel stored
         return ARG_ERROR("lbm_sim_set_walls: the fused kernel does not maintain the ghosts of the fastest axis "
@@ -801,6 +817,46 @@ extern "C" int lbm_sim_set_walls(lbm_sim* s, lbmk_launch_walls_fn launcher, cons
     // ghost values of the current array were produced under the previous setting
     s->ghost_fresh = 0;
     drop_graph(s);
+    return 0;
+}
+
+extern "C" int lbm_sim_set_tasks(lbm_sim* s, lbmk_launch_tasks_fn launcher, int64_t ntasks, int64_t nblocks,
+                                 const int32_t* block_ptr, const uint32_t* code, const int64_t* l0,
+                                 const int64_t* l1, const double* dist, const int32_t* ibc, const int64_t* entry,
+                                 int ngroups_y, int ngroups_x, int tx) {
+    if (!s) return ARG_ERROR("null sim");
+    cudaStreamSynchronize(s->stream);
+    free_tasks(s);
+    drop_graph(s);
+    if (ntasks < 0) return 0;
+    if (!launcher || nblocks <= 0 || !block_ptr || (ntasks > 0 && (!code || !l0 || !l1 || !dist || !ibc || !entry)))
+        return ARG_ERROR("lbm_sim_set_tasks: null argument");
+    if (s->walls_fn) return ARG_ERROR("lbm_sim_set_tasks: not combined with lbm_sim_set_walls");
+    if (block_ptr[0] != 0 || block_ptr[nblocks] != ntasks) return ARG_ERROR("lbm_sim_set_tasks: block_ptr must span [0, ntasks]");
+    std::vector<const double*> rhs((size_t)ntasks, nullptr);
+    for (int64_t t = 0; t < ntasks; ++t) {
+        if (ibc[t] < 0 || ibc[t] >= (int)s->bcs.size()) return ARG_ERROR("lbm_sim_set_tasks: no such method");
+        const BcMethod& b = s->bcs[ibc[t]];
+        if (entry[t] < 0 || entry[t] >= b.ncond) return ARG_ERROR("lbm_sim_set_tasks: entry out of range");
+        const unsigned kind = code[t] >> 16;
+        if ((int)kind != b.kind) return ARG_ERROR("lbm_sim_set_tasks: kind differs from the method's");
+        rhs[(size_t)t] = (b.kind == LBM_BC_NEUMANN) ? nullptr : b.rhs + entry[t];
+    }
+    lbmk_tasks tk;
+    memset(&tk, 0, sizeof(tk));
+    cudaError_t e = upload((int**)&tk.block_ptr, (const int*)block_ptr, nblocks + 1);
+    if (e == cudaSuccess) e = upload((unsigned**)&tk.code, (const unsigned*)code, ntasks);
+    if (e == cudaSuccess) e = upload((long long**)&tk.l0, (const long long*)l0, ntasks);
+    if (e == cudaSuccess) e = upload((long long**)&tk.l1, (const long long*)l1, ntasks);
+    if (e == cudaSuccess) e = upload((const double***)&tk.rhs, (const double* const*)rhs.data(), ntasks);
+    if (e == cudaSuccess) e = upload((double**)&tk.dist, dist, ntasks);
+    tk.ngroups_y = ngroups_y; tk.ngroups_x = ngroups_x; tk.tx = tx;
+    s->tasks = tk;
+    s->tasks_fn = launcher;       // (set before a failure is reported so that free_tasks releases the parts)
+    if (e != cudaSuccess) {
+        free_tasks(s);
+        return set_error(-(int)e, "lbm_sim_set_tasks", cudaGetErrorString(e));
+    }
     return 0;
 }
 
@@ -955,7 +1011,16 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
                 s->waits += 1;
                 s->waited = 1;
             }
+        } else if (s->xchg_inflight && s->ghost_fresh) {
+            // NCCL halo, steady state: the slab-face planes of this array were exchanged on the
+            // communication stream while the previous step computed its inner cells
+            CUDA_TRY(cudaStreamWaitEvent(st, s->ev_comm, 0));
+            s->xchg_inflight = 0;
         } else {
+            if (s->xchg_inflight) {               // stale ghosts (outside write): redo it after the one in flight
+                CUDA_TRY(cudaStreamWaitEvent(st, s->ev_comm, 0));
+                s->xchg_inflight = 0;
+            }
             int rc = exchange_slabs(s, f, st);
             if (rc) return rc;
             if (s->peers_ready && s->waits < s->signals) {
@@ -977,8 +1042,10 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
 static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) {
     int rc = ghost_update(s, f, st);
     if (rc) return rc;
-    rc = apply_bcs(s, f, st);
-    if (rc) return rc;
+    if (!s->tasks_fn) {          // with a task table the fused kernel evaluates the entries itself
+        rc = apply_bcs(s, f, st);
+        if (rc) return rc;
+    }
     double scal[32];
     for (int i = 0; i < s->d.nscalars; ++i) scal[i] = s->d.scalars[i];
     if (s->d.t_index >= 0 && s->d.t_index < s->d.nscalars) scal[s->d.t_index] = t;
@@ -1007,12 +1074,42 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
         pr.pstride_hi = s->peer_pstride[1];
         pr.nin_lo = s->peer_nin_lo;
     }
-    if (s->walls_fn)
-        rc = s->walls_fn(f, fnew, &g, scal, s->peers_ready ? &pr : nullptr, &s->walls, (void*)st);
-    else if (s->peers_ready)
-        rc = s->d.one_time_step_peers(f, fnew, &g, scal, &pr, (void*)st);
-    else
-        rc = s->d.one_time_step(f, fnew, &g, scal, (void*)st);
+    auto launch_fused = [&](const lbmk_grid& gg) -> int {
+        if (s->tasks_fn)
+            return s->tasks_fn(f, fnew, &gg, scal, s->peers_ready ? &pr : nullptr, &s->tasks, (void*)st);
+        if (s->walls_fn)
+            return s->walls_fn(f, fnew, &gg, scal, s->peers_ready ? &pr : nullptr, &s->walls, (void*)st);
+        if (s->peers_ready) return s->d.one_time_step_peers(f, fnew, &gg, scal, &pr, (void*)st);
+        return s->d.one_time_step(f, fnew, &gg, scal, (void*)st);
+    };
+    const int ax = s->slab_axis, wx = s->d.vmax[ax];
+    const bool split = s->nranks > 1 && !s->peers_ready && s->overlap && s->comm && wx > 0 &&
+                       g.hi[ax] - g.lo[ax] > 4 * wx && !(s->tasks_fn && ax != 0);
+    if (split) {
+        // NCCL halo with overlap: the cells within `wx` of the slab faces first, then their planes travel
+        // on the communication stream (they are the ghost planes of the neighbours' NEXT step) while
+        // the inner cells are computed.  BC kernels of the next step run after the exchange, in the
+        // reference's order (simulation.py:384-390).
+        lbmk_grid lo = g, hi = g, in = g;
+        lo.hi[ax] = g.lo[ax] + wx;
+        hi.lo[ax] = g.hi[ax] - wx;
+        in.lo[ax] = g.lo[ax] + wx;
+        in.hi[ax] = g.hi[ax] - wx;
+        rc = launch_fused(lo);
+        if (rc == 0) rc = launch_fused(hi);
+        if (rc == 0) {
+            CUDA_TRY(cudaEventRecord(s->ev_ready, st));
+            CUDA_TRY(cudaStreamWaitEvent(s->comm_stream, s->ev_ready, 0));
+            int rx = exchange_slabs(s, fnew, s->comm_stream);
+            if (rx) return rx;
+            CUDA_TRY(cudaEventRecord(s->ev_comm, s->comm_stream));
+            s->xchg_inflight = 1;
+            rc = launch_fused(in);
+            s->launches += 2;
+        }
+    } else {
+        rc = launch_fused(g);
+    }
     if (rc) return set_error(rc, "one_time_step kernel launch", cudaGetErrorString((cudaError_t)(-rc)));
     if (ev1) cudaEventRecord(ev1, st);
     s->launches += 1;
@@ -1235,6 +1332,7 @@ extern "C" int lbm_sim_comm_init(lbm_sim* s, int rank, int nranks, const void* i
     nccl_uid id;
     memcpy(&id, id128, 128);
     NCCL_TRY(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
+    if (getenv("PYLBM_B200_NO_OVERLAP")) s->overlap = 0;   // debugging aid: exchange on the compute stream
     s->wrap_mask &= ~(1 << s->slab_axis);   // the slab axis is exchanged between ranks, not wrapped
     s->ghost_fresh = 0;
     drop_graph(s);

@@ -219,6 +219,17 @@ typedef struct {       // bounce-back walls normal to the fastest axis handled b
     int neg_hi;
     double rhs[64];    // right-hand side per LOADED population (the one moving towards the wall)
 } lbmk_walls;
+extern "C" {
+typedef struct {       // boundary entries evaluated by the pulling thread (see lbmk.h)
+    const int* block_ptr;           // [nblocks + 1] first task of every 128-thread block
+    const unsigned* code;           // thread | population << 8 | kind << 16
+    const long long* l0;            // element positions read in the INPUT array
+    const long long* l1;
+    const double* const* rhs;       // address of the right-hand side of the entry (NULL: none)
+    const double* dist;             // Bouzidi coefficient
+    int ngroups_y, ngroups_x, tx;   // launch geometry the table was built for
+} lbmk_tasks;
+}
 #define SLAB %(slab)d
 
 typedef %(storage)s real_f;   // storage type of the populations in HBM
@@ -246,6 +257,7 @@ struct lbmk_offs_%(name)s {
 lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g,
     const lbmk_offs_%(name)s offs%(peer_param)s%(scalar_params)s)
 {
+    constexpr int NQ_ = %(nin)d; (void)NQ_;
     typedef %(tc)s real_c;   // arithmetic type of this kernel
     // 3-D grid: x = chunk of the fastest axis, y = group of `ty` rows of axis 1, z = index of axis 0
     // (no integer division in the prologue; tx is a power of two)
@@ -262,7 +274,7 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
     }
     const int i1 = g.lo[1] + (int)(by * ty + (tid >> txshift));
     const int i0 = g.lo[0] + (int)bz;
-    if (i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]) return;
+%(guard)s
     const long long rowstride = g.pitch;
     const long long planestride = (long long)g.n[1] * g.pitch;
     const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
@@ -271,10 +283,12 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
     unsigned long long pout = (unsigned long long)(fout + cell);
     asm volatile("" : "+l"(pin), "+l"(pout));   // keep `pointer + constant-bank offset` as the address form
 %(loads)s
+%(overrides)s
 %(prologue)s
 %(body)s
 %(stores)s
 %(images)s
+%(guard_end)s
 }
 
 %(launch_head)s
@@ -364,6 +378,54 @@ _IMAGES_LAUNCH = r"""
 """
 
 
+_GUARD_PLAIN = "    if (i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]) return;"
+
+# Boundary entries folded into the fused kernel (TASKS instantiation).  Entry `f_k(c_out) = value` of a
+# boundary method is read by exactly one pull: cell c_out + v_k, population k.  Instead of a list kernel
+# storing the value into the ghost / solid cell and this kernel pulling it back, the block that owns the
+# pulling cell evaluates its entries here -- one entry per thread, in parallel, same explicit
+# round-to-nearest arithmetic as the list kernel k_bc (runtime) -- and hands the values to the owning
+# threads through shared memory.  The host (boundary.plan_tasks) proves that no entry reads what another
+# entry stores, so the input array alone determines every value.
+_GUARD_TASKS = r"""    const bool active_ = !(i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]);
+    if (!TASKS && !active_) return;
+    unsigned long long tmask_ = 0ull;
+    extern __shared__ __align__(16) unsigned char lbmk_smem_[];
+    real_c* const sm_val_ = (real_c*)lbmk_smem_;                                  // [NQ][LBMK_BLOCK]
+    unsigned long long* const sm_mask_ = (unsigned long long*)(sm_val_ + NQ_ * LBMK_BLOCK);
+    if (TASKS) {
+        const long long bid_ = ((long long)(i0 - g.w[0]) * tasks.ngroups_y + by) * tasks.ngroups_x + blockIdx.x;
+        const int t0_ = __ldg(tasks.block_ptr + bid_), t1_ = __ldg(tasks.block_ptr + bid_ + 1);
+        if (t1_ > t0_) {                                   // block-uniform
+            sm_mask_[tid] = 0ull;
+            __syncthreads();
+            for (int t = t0_ + (int)tid; t < t1_; t += LBMK_BLOCK) {
+                const unsigned code = __ldg(tasks.code + t);
+                const unsigned kind = code >> 16, kk = (code >> 8) & 255u, th = code & 255u;
+                const double a = (double)__ldg(fin + __ldg(tasks.l0 + t));
+                double v = a;                                                  // Neumann
+                if (kind != 4u) {
+                    const double r = __ldg(tasks.rhs[t]);
+                    if (kind == 0u) v = __dadd_rn(a, r);                       // bounce-back
+                    else if (kind == 1u) v = __dadd_rn(-a, r);                 // anti-bounce-back
+                    else {
+                        const double b = (double)__ldg(fin + __ldg(tasks.l1 + t));
+                        const double d = __ldg(tasks.dist + t);
+                        const double far = __dmul_rn(__dsub_rn(1.0, d), b);
+                        const double near = __dmul_rn(d, a);
+                        v = __dadd_rn(__dadd_rn(far, kind == 2u ? near : -near), r);   // Bouzidi (anti-)bounce-back
+                    }
+                }
+                sm_val_[kk * LBMK_BLOCK + th] = (real_c)(%(tin)s)v;       // rounded like the stored value
+                atomicOr(sm_mask_ + th, 1ull << kk);
+            }
+            __syncthreads();
+            tmask_ = sm_mask_[tid];
+        }
+    }
+    if (active_) {"""
+
+
 def _inline_image(v, k, slab, tout):
     """store suffix for the image that only crosses the FASTEST axis (two lanes of every row): done
     with the main store from the register value -- no re-read, no divergent tail.  In the WALLZ
@@ -419,9 +481,16 @@ def _canonical(offset):
 
 
 _LAUNCH_HEAD = 'extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)'
-_LAUNCH_HEAD_WALLS = ('extern "C" int lbmk_%(name)s_walls(const void* fin, void* fout, const lbmk_grid* g, '
-                      'const double* scalars, const lbmk_peers* peers, const lbmk_walls* walls, void* stream)')
+_LAUNCH_HEAD_WALLS = ('static int lbmk_launch_%(name)s_(const void* fin, void* fout, const lbmk_grid* g, '
+                      'const double* scalars, const lbmk_peers* peers, const lbmk_walls* walls, '
+                      'const lbmk_tasks* tasks, void* stream)')
 _LAUNCH_TAIL_WALLS = """
+extern "C" int lbmk_%(name)s_tasks(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                                   const lbmk_peers* peers, const lbmk_tasks* tasks, void* stream)
+{
+    if (!tasks) return lbmk_%(name)s_walls(fin, fout, g, scalars, peers, nullptr, stream);
+    return lbmk_launch_%(name)s_(fin, fout, g, scalars, peers, nullptr, tasks, stream);
+}
 extern "C" int lbmk_%(name)s_peers(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
                                    const lbmk_peers* peers, void* stream)
 {
@@ -432,15 +501,34 @@ extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, co
     return lbmk_%(name)s_walls(fin, fout, g, scalars, nullptr, nullptr, stream);
 }
 """
+_LAUNCH_TAIL_WALLS = """
+extern "C" int lbmk_%(name)s_walls(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
+                                   const lbmk_peers* peers, const lbmk_walls* walls, void* stream)
+{
+    return lbmk_launch_%(name)s_(fin, fout, g, scalars, peers, walls, nullptr, stream);
+}""" + _LAUNCH_TAIL_WALLS
 _CALL_PLAIN = """    lbmk_kernel_%(name)s<<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
         (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs%(scalar_args)s);"""
 _CALL_WALLS = """    const lbmk_peers pr_ = peers ? *peers : lbmk_peers{nullptr, nullptr, 0, 0, 0};
-    if (walls)
-        lbmk_kernel_%(name)s<true><<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
-            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, *walls%(scalar_args)s);
+    const lbmk_tasks notasks_ = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
+    if (tasks) {
+        // the table maps cells to (block, thread) of THIS launch geometry
+        if (walls || tasks->tx != g->tx || g->lo[1] != g->w[1] || g->lo[2] != g->w[2] || offs.fold
+            || tasks->ngroups_x != (int)grid.x || tasks->ngroups_y != (int)grid.y) return -4;
+        const size_t smem_ = (size_t)%(nin)d * LBMK_BLOCK * sizeof(real_c_%(name)s) + LBMK_BLOCK * sizeof(unsigned long long);
+        static bool attr_ = false;
+        if (!attr_ && smem_ > 48 * 1024) {
+            cudaFuncSetAttribute(lbmk_kernel_%(name)s<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
+            attr_ = true;
+        }
+        lbmk_kernel_%(name)s<false, true><<<grid, LBMK_BLOCK, smem_, (cudaStream_t)stream>>>(
+            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, lbmk_walls{}, *tasks%(scalar_args)s);
+    } else if (walls)
+        lbmk_kernel_%(name)s<true, false><<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
+            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, *walls, notasks_%(scalar_args)s);
     else
-        lbmk_kernel_%(name)s<false><<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
-            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, lbmk_walls{}%(scalar_args)s);"""
+        lbmk_kernel_%(name)s<false, false><<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
+            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, lbmk_walls{}, notasks_%(scalar_args)s);"""
 
 
 def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0, compute="double"):
@@ -453,7 +541,15 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
     tout = "real_m" if ir.out_array == "m" else "real_f"
     loads = []
     for k, sym in enumerate(ir.in_syms):
-        loads.append("    const real_c %s = (real_c)__ldg((const %s*)(pin + offs.in[%d]));" % (sym, tin, k))
+        loads.append("    %sreal_c %s = (real_c)__ldg((const %s*)(pin + offs.in[%d]));"
+                     % ("" if images else "const ", sym, tin, k))
+    overrides = ""
+    if images:
+        lines = ["    if (TASKS && tmask_) {   // pulled values that are boundary entries of this step"]
+        for k, sym in enumerate(ir.in_syms):
+            lines.append("        if (tmask_ & (1ull << %d)) %s = sm_val_[%d * LBMK_BLOCK + tid];" % (k, sym, k))
+        lines.append("    }")
+        overrides = "\n".join(lines)
     body = ["    const real_c %s = %s;" % (lhs, pr.doprint(rhs)) for lhs, rhs in temps]
     if images:
         vels = [tuple(-o for o in _canonical(off)) for off in ir.in_offsets]
@@ -488,10 +584,15 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         loads="\n".join(loads),
         images=_images_code([tuple(-o for o in _canonical(off)) for off in ir.in_offsets], tout, slab) if images else "",
         prologue=(_IMAGES_PROLOGUE % dict(tout=tout)) if images else "",
-        template="template <bool WALLZ>\n" if images else "",
-        peer_param=", const lbmk_peers pr, const lbmk_images img, const lbmk_walls walls" if images else "",
+        template="template <bool WALLZ, bool TASKS>\n" if images else "",
+        peer_param=(", const lbmk_peers pr, const lbmk_images img, const lbmk_walls walls, const lbmk_tasks tasks"
+                    if images else ""),
+        guard=(_GUARD_TASKS % dict(tin=tin)) if images else _GUARD_PLAIN,
+        guard_end="    }" if images else "",
+        overrides=overrides,
         images_launch=(_IMAGES_LAUNCH % dict(nout=len(outs), tout=tout, sym_table=sym_table)) if images else "",
-        kernel_call=(_CALL_WALLS if images else _CALL_PLAIN) % dict(name=ir.name, tin=tin, tout=tout, scalar_args=scal_args),
+        kernel_call=(_CALL_WALLS if images else _CALL_PLAIN) % dict(name=ir.name, tin=tin, tout=tout,
+                                                                    scalar_args=scal_args, nin=nq),
         launch_head=(_LAUNCH_HEAD_WALLS if images else _LAUNCH_HEAD) % dict(name=ir.name),
         launch_tail=(_LAUNCH_TAIL_WALLS % dict(name=ir.name)) if images else "",
         body="\n".join(body),
@@ -504,7 +605,7 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
     return src, (add, mul, div)
 
 
-_C_KEYWORDS = {"lambda", "double", "int", "float", "long", "short", "register", "const", "void", "auto", "g", "fin", "fout", "cell", "tid",
+_C_KEYWORDS = {"tasks", "active_", "tmask_", "lambda", "double", "int", "float", "long", "short", "register", "const", "void", "auto", "g", "fin", "fout", "cell", "tid",
                "pin", "pout", "offs", "pr", "tx", "ty", "i0", "i1", "i2", "d0", "d1", "d2", "real_c"}
 
 

@@ -259,7 +259,8 @@ class CudaEngine:
             method.fix_iload()
             method.set_rhs()
             method.prepare_device(F)
-        masks = self._plan_walls()
+        tasks = self._plan_tasks()
+        masks = self._plan_walls() if tasks is None else [None] * len(self.bc.methods)
         # device methods in application order; the entries a wall plan takes out of a method follow it
         # immediately as a stale-only method (same place in the sequence as in the reference)
         info = []
@@ -296,8 +297,39 @@ class CudaEngine:
                                                groups.ctypes.data_as(ctypes.POINTER(ctypes.c_int))),
                          "lbm_sim_bc_groups")
             self.bc.groups = groups
+        if tasks is not None:
+            ptr = lambda a: a.ctypes.data
+            rt.check(lib.lbm_sim_set_tasks(
+                self._handle, self.kernels.address("one_time_step_tasks"), tasks["ntasks"], tasks["nblocks"],
+                ptr(tasks["block_ptr"]), ptr(tasks["code"]), ptr(tasks["l0"]), ptr(tasks["l1"]), ptr(tasks["dist"]),
+                ptr(tasks["ibc"]), ptr(tasks["entry"]), tasks["ngroups_y"], tasks["ngroups_x"], tasks["tx"]),
+                "lbm_sim_set_tasks")
+        self.bc.tasks = None if tasks is None else {k: tasks[k] for k in ("ntasks", "nentries", "nblocks")}
         self._time_dependent = any(m.is_time_dependent for m in self.bc.methods)
         self._need_init = False
+
+    def _plan_tasks(self):
+        """boundary entries evaluated by the fused kernel itself (boundary.plan_tasks): one launch per
+        step.  Chosen for lattices where the list kernels are a visible share of the step -- small
+        lattices (launch-bound) and lattices with few entries per cell; big wall-dominated boxes keep the
+        list kernels / the fused walls (measured).  PYLBM_B200_TASKS=0/1 forces it off / on."""
+        from .boundary import plan_tasks
+
+        self.bc.walls = None
+        mode = os.environ.get("PYLBM_B200_TASKS", "auto")
+        if mode == "0" or not self.bc.methods:
+            return None
+        F = self.container.F
+        cells = float(np.prod(self.domain.shape_in))
+        nentries = sum(len(m._keep[0]) for m in self.bc.methods)
+        if mode != "1" and not (cells <= 2 ** 22 or nentries <= 0.03 * cells):
+            return None
+        info = []
+        for method in self.bc.methods:
+            store, l0, l1, _, dist, level_ptr, two_phase = method._keep
+            info.append({"kind": method.kind, "store": store, "loads": [l0] + ([l1] if l1 is not None else []),
+                         "dist": dist, "single": len(level_ptr) == 2 and not int(two_phase[0])})
+        return plan_tasks(info, F, self.scheme.stencil.get_all_velocities())
 
     def _plan_walls(self):
         """bounce-back walls of the fastest axis applied by the fused kernel (boundary.plan_walls)."""

@@ -35,6 +35,15 @@ def _roundup(n, m):
     return (n + m - 1) // m * m
 
 
+def block_tx(n_fast):
+    """threads of a 128-thread block laid along the fastest axis (power of two): whole rows of short
+    lattices share a block (lbmk_grid.tx)."""
+    tx = 128
+    while tx > 1 and tx // 2 >= n_fast:
+        tx //= 2
+    return tx
+
+
 class _ConsmMixin:
     def set_conserved_moments(self, consm):
         for k, v in consm.items():
@@ -82,6 +91,7 @@ class Layout:
         self.lead = (align - w[2]) % align
         self.pstride = _roundup(self.lead + n[0] * n[1] * self.pitch, align)
         self.canonical_n, self.canonical_vmax = n, w
+        self.tx = block_tx(n[2])
 
     def positions(self, index):
         """element positions of entries [k, ix(, iy(, iz))] given as an integer array (dim+1, n)."""
@@ -157,10 +167,7 @@ class DeviceArray(_ConsmMixin):
             self.grid.hi[a] = n[a]
             self.grid.w[a] = w[a]
         self.grid.wrap = 0
-        tx = 128
-        while tx > 1 and tx // 2 >= n[2]:
-            tx //= 2
-        self.grid.tx = tx
+        self.tx = self.grid.tx = block_tx(n[2])
         self.grid.pitch, self.grid.lead, self.grid.pstride = pitch, lead, pstride
 
         ptr = ctypes.c_void_p()

@@ -270,6 +270,8 @@ def test_walls_in_the_fused_kernel_are_bit_identical_to_the_list_kernel(name, kw
     import pylbm_b200
     from pylbm_b200 import cases
 
+    monkeypatch.setenv("PYLBM_B200_TASKS", "0")        # (small lattices would take the task table instead)
+
     def run(walls):
         if walls:
             monkeypatch.delenv("PYLBM_B200_NO_WALLS", raising=False)
@@ -306,11 +308,54 @@ def test_walls_in_the_fused_kernel_are_bit_identical_to_the_list_kernel(name, kw
             assert err <= TOL_F64, (str(key), err)
 
 
-def test_wall_plan_is_refused_when_it_would_change_results():
+def test_wall_plan_is_refused_when_it_would_change_results(monkeypatch):
     """Bouzidi walls, Neumann faces or periodic boxes never get the fused-kernel walls."""
     import pylbm_b200
     from pylbm_b200 import cases
 
+    monkeypatch.setenv("PYLBM_B200_TASKS", "0")
+
     for name, kw in [("karman_d2q9", dict(nx=64, ny=32)), ("shallow_water_d2q4", dict(n=32)), ("heat_d2q5", dict(n=32))]:
         sim = pylbm_b200.Simulation(cases.CASES[name](**kw))
         assert sim.bc.walls is None, name
+
+
+TASK_CASES = [PARITY_CASES[i] for i in (0, 1, 4, 5, 6, 8, 10)]
+
+
+@pytest.mark.parametrize("name,kw", TASK_CASES, ids=[c[0] + "-" + "x".join(str(v) for v in c[1].values()) for c in TASK_CASES])
+@pytest.mark.parametrize("dtype", ["float64", "float32"])
+def test_boundary_entries_in_the_fused_kernel_are_bit_identical_to_the_list_kernels(name, kw, dtype, monkeypatch):
+    """boundary entries evaluated by the fused kernel (task table, boundary.plan_tasks: ONE launch per
+    step) against the list kernels (one launch per method + fused kernel): same arithmetic, so the
+    interior populations must be IDENTICAL -- single steps, graph pairs, a stand-alone
+    boundary_condition() in between, an outside write of F; time-dependent right-hand sides included
+    (rayleigh_benard)."""
+    import pylbm_b200
+    from pylbm_b200 import cases, runtime as rt
+
+    def run(tasks):
+        monkeypatch.setenv("PYLBM_B200_TASKS", "1" if tasks else "0")
+        monkeypatch.setenv("PYLBM_B200_NO_WALLS", "1")
+        sim = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw), dtype=dtype)
+        assert (sim.bc.tasks is not None) == tasks
+        before = rt.lib().lbm_sim_launch_count(sim._handle)
+        sim.run(8)
+        launches = rt.lib().lbm_sim_launch_count(sim._handle) - before
+        sim.one_time_step()
+        sim.boundary_condition()
+        sim.F_halo[1] = sim.F_halo[1]
+        sim.run(5)
+        sim.one_time_step()
+        return sim, launches
+
+    (a, la), (b, lb) = run(True), run(False)
+    assert a.bc.tasks["ntasks"] > 0
+    if not a._time_dependent:
+        assert la < lb            # first step: copy kernels for the periodic axes, then 1 launch per step
+    inner = (slice(None),) + tuple(slice(v, -v) for v in a.domain.stencil.vmax)
+    fluid = a.domain.in_or_out[inner[1:]] == a.domain.valin
+    Fa, Fb = a.container.F.get()[inner], b.container.F.get()[inner]
+    assert np.array_equal(Fa[:, fluid], Fb[:, fluid])
+    for key in a.scheme.consm:
+        assert np.array_equal(a.m[key][fluid], b.m[key][fluid])

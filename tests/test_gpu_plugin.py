@@ -156,7 +156,7 @@ def test_reference_protocols_on_the_cuda_simulation(cuda):
     a.container.m.set(np.zeros_like(m_engine))
     a.algo.call_function("f2m", a)
     assert np.array_equal(a.container.m.get(), m_engine)
-    mass = [k for k in a.scheme.consm if str(k) == "mass"][0]
+    mass = list(a.scheme.consm)[0]            # the density (first conserved moment)
     assert a.m[mass].shape == tuple(a.domain.shape_in) and a.m_halo[mass].shape == tuple(a.domain.shape_halo)
     assert a.F[0].shape == tuple(a.domain.shape_in)
     assert abs(a.m[mass].mean() - 1.0) < 1e-3
