@@ -139,6 +139,17 @@ int lbm_sim_add_bc(lbm_sim* sim, int kind, int64_t ncond, const int64_t* istore,
                    const double* dist, int nlevels, const int64_t* level_ptr,
                    const int* two_phase);
 int lbm_sim_set_rhs(lbm_sim* sim, int ibc, const double* rhs_host);
+/* Time-dependent boundary values without a host round trip (reference: boundary.py:307-321 update_feq +
+ * 421-427 set_rhs, both NumPy on the host every step).  lbm_sim_upload_rows brings the moments the
+ * user's callback wrote (small host block, `height` rows of `width` bytes) to the device on the
+ * simulation's stream through page-locked staging, without stalling the host; the caller then enqueues
+ * the equilibrium / m2f kernels of the kernel library on lbm_sim_stream() and lbm_sim_rhs_update, which
+ * recomputes rhs[dst[j]] = feq[a[j]] + sign * feq[b[j]] (sign = -1 bounce-back kinds, +1 anti-bounce-back
+ * kinds) for j < count in the method's DEVICE list.  a, b, dst, feq are DEVICE pointers. */
+int lbm_sim_upload_rows(lbm_sim* sim, void* dst_dev, uint64_t dpitch, const void* src_host, uint64_t spitch,
+                        uint64_t width, uint64_t height);
+int lbm_sim_rhs_update(lbm_sim* sim, int ibc, int64_t count, const int64_t* a_dev, const int64_t* b_dev,
+                       const int64_t* dst_dev, double sign, const double* feq_dev);
 /* flag != 0: method `ibc` is applied only when the ghost layers of the current array are NOT the ones
  * the previous fused launch produced (first step, after lbm_sim_invalidate_ghosts).  Used for the
  * entries of the walls handed to lbm_sim_set_walls: in steady state the fused kernel has already

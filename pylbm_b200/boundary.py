@@ -21,6 +21,7 @@ scatter.  Bouzidi bounce-back reads a snapshot taken when the method starts
 """
 
 import collections
+import ctypes
 
 import numpy as np
 
@@ -577,6 +578,70 @@ class BoundaryMethod:
     def is_time_dependent(self):
         return len(self.func) > 0
 
+    rhs_sign = None          # rhs = feq[k] + rhs_sign * feq[ksym] (None: the kind has no right-hand side)
+
+    def prepare_time_bc(self, simulation):
+        """device side of the time-dependent labels (after move2gpu): per label, scratch arrays for the
+        moments / equilibrium populations at the wall points and the index lists of
+        `rhs = feq[k] -/+ feq[ksym]` in the order of the device list."""
+        from .storage import DeviceArray
+
+        self._time_plans = []
+        if not self.func or self.rhs_sign is None or self.device_index is None:
+            return
+        nv = simulation.container.nv
+        sym = np.asarray(self.stencil.get_symmetric())
+        inverse = np.empty(self.istore.shape[0], dtype=np.int64)
+        inverse[:] = -1
+        inverse[self._order] = np.arange(self._order.size)
+        for idx in self.indices:
+            ncond = idx.size
+            dm = DeviceArray(nv, (ncond,), [0], "f64")
+            df = DeviceArray(nv, (ncond,), [0], "f64")
+            k = self.istore[idx, 0].astype(np.int64)
+            col = np.arange(ncond, dtype=np.int64)
+            dst = inverse[idx]
+            live = dst >= 0                     # entries dropped from the device list (duplicates)
+            a = df.positions(np.stack([k, col]))[live]
+            b = df.positions(np.stack([sym[k], col]))[live]
+            lists = []
+            for arr in (a, b, dst[live]):
+                arr = np.ascontiguousarray(arr, dtype=np.int64)
+                ptr = ctypes.c_void_p()
+                rt.check(rt.lib().lbm_malloc(ctypes.byref(ptr), max(8, arr.nbytes)), "lbm_malloc")
+                rt.check(rt.lib().lbm_memcpy_h2d(ptr, arr.ctypes.data, arr.nbytes), "h2d")
+                lists.append(ptr.value)
+            self._time_plans.append((dm, df, lists, int(live.sum())))
+
+    def update_feq_device(self, simulation):
+        """time-dependent boundary values (reference: boundary.py:307-321 + set_rhs 421-427) with only
+        the user's callback on the host: its moments are uploaded asynchronously, equilibrium + m2f run
+        on the simulation's stream and the right-hand sides are recomputed in the device list -- no
+        device-to-host copy, no synchronisation."""
+        lib = rt.lib()
+        handle = simulation._handle
+        kernels = simulation._kernels_f64()
+        stream = lib.lbm_sim_stream(handle)
+        for i, func in enumerate(self.func):
+            dm, df, lists, count = self._time_plans[i]
+            m = self.m[i]
+            func(self.f[i], m, simulation.t, *self.args[i])
+            host = m.array.reshape(dm.nv, -1)
+            rt.check(lib.lbm_sim_upload_rows(handle, dm.ptr + dm.lead * 8, dm.pstride * 8, host.ctypes.data,
+                                             host.strides[0], host.shape[1] * 8, dm.nv), "lbm_sim_upload_rows")
+            kernels.launch("equilibrium", dm.ptr, dm.ptr, dm.grid, simulation._scalar_values("equilibrium"), stream)
+            kernels.launch("m2f", dm.ptr, df.ptr, dm.grid, simulation._scalar_values("m2f"), stream)
+            rt.check(lib.lbm_sim_rhs_update(handle, self.device_index, count, lists[0], lists[1], lists[2],
+                                            float(self.rhs_sign), df.ptr), "lbm_sim_rhs_update")
+
+    def __del__(self):
+        for plan in getattr(self, "_time_plans", ()):
+            for ptr in plan[2]:
+                try:
+                    rt.lib().lbm_free(ptr)
+                except Exception:
+                    pass
+
     # ---- device side ---------------------------------------------------------
     def device_lists(self, array):
         """positions in the padded device layout + level schedule (after fix_iload)."""
@@ -640,6 +705,8 @@ class BounceBack(BoundaryMethod):
         v = self.stencil.get_all_velocities()
         self.iload.append(np.concatenate([ksym, self.istore[1:] + v[k].T]))
 
+    rhs_sign = -1
+
     def set_rhs(self):
         self._sym_difference(-1)
 
@@ -678,6 +745,8 @@ class BouzidiBounceBack(BoundaryMethod):
         self.iload.append(iload1)
         self.iload.append(iload2)
 
+    rhs_sign = -1
+
     def set_rhs(self):
         self._sym_difference(-1)
 
@@ -686,6 +755,7 @@ class AntiBounceBack(BounceBack):
     """f_k(store) = -f_ksym(store + v_k) + rhs (reference: boundary.py:626-684)."""
 
     kind = rt.BC_ANTI_BOUNCE_BACK
+    rhs_sign = +1
 
     def set_rhs(self):
         self._sym_difference(+1)
@@ -696,6 +766,7 @@ class BouzidiAntiBounceBack(BouzidiBounceBack):
 
     kind = rt.BC_BOUZIDI_ANTI_BOUNCE_BACK
     snapshot = False
+    rhs_sign = +1
 
     def set_rhs(self):
         self._sym_difference(+1)

@@ -586,6 +586,10 @@ struct lbm_sim {
     int rank = 0, nranks = 1;
     int slab_axis = 0;
     // direct NVLink halo (CUDA IPC): peer arrays [side lo/hi][buffer A/B], arrival counters
+    void* up_buf[2] = {nullptr, nullptr};         // page-locked staging of lbm_sim_upload_rows
+    uint64_t up_bytes[2] = {0, 0};
+    cudaEvent_t up_event[2] = {nullptr, nullptr};
+    int up_next = 0;
     int xchg_inflight = 0;                        // NCCL halo: the exchange for the CURRENT f was issued on
                                                   // comm_stream during the previous step (ev_comm marks its end)
     int overlap = 1;                              // NCCL halo: exchange of step s+1 || inner cells of step s
@@ -709,6 +713,10 @@ extern "C" void lbm_sim_destroy(lbm_sim* s) {
     if (s->wait_err) cudaFreeHost(s->wait_err);
     if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
     free_tasks(s);
+    for (int i = 0; i < 2; ++i) {
+        if (s->up_buf[i]) cudaFreeHost(s->up_buf[i]);
+        if (s->up_event[i]) cudaEventDestroy(s->up_event[i]);
+    }
     for (auto& b : s->bcs) free_bc(b);
     cudaFree(s->scratch);
     for (auto e : s->prof_events) cudaEventDestroy(e);
@@ -891,6 +899,59 @@ extern "C" int lbm_sim_set_rhs(lbm_sim* s, int ibc, const double* rhs_host) {
     if (b.ncond == 0 || !b.rhs) return 0;
     CUDA_TRY(cudaMemcpyAsync(b.rhs, rhs_host, (size_t)b.ncond * sizeof(double), cudaMemcpyHostToDevice, s->stream));
     CUDA_TRY(cudaStreamSynchronize(s->stream));  // rhs_host may be pageable / reused by the caller
+    return 0;
+}
+
+// right-hand sides recomputed on the device from wall equilibria: rhs[dst[j]] = feq[a[j]] + sign*feq[b[j]]
+// (reference: boundary.py:421-427 `rhs = feq[k] - feq[ksym]`, 637-643 with +; one IEEE operation each)
+__global__ void k_rhs_from_feq(double* __restrict__ rhs, const double* __restrict__ feq, const long long* __restrict__ a,
+                               const long long* __restrict__ b, const long long* __restrict__ dst, double sign,
+                               long long count) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= count) return;
+    rhs[dst[j]] = __dadd_rn(feq[a[j]], __dmul_rn(sign, feq[b[j]]));
+}
+
+extern "C" int lbm_sim_rhs_update(lbm_sim* s, int ibc, int64_t count, const int64_t* a_dev, const int64_t* b_dev,
+                                  const int64_t* dst_dev, double sign, const double* feq_dev) {
+    if (!s || ibc < 0 || ibc >= (int)s->bcs.size()) return ARG_ERROR("lbm_sim_rhs_update: no such method");
+    if (count <= 0) return 0;
+    BcMethod& bm = s->bcs[ibc];
+    if (!bm.rhs || !a_dev || !b_dev || !dst_dev || !feq_dev || count > bm.ncond)
+        return ARG_ERROR("lbm_sim_rhs_update: null argument or more entries than the method has");
+    if (sign != 1.0 && sign != -1.0) return ARG_ERROR("lbm_sim_rhs_update: sign must be +1 or -1");
+    k_rhs_from_feq<<<(unsigned)((count + 127) / 128), 128, 0, s->stream>>>(
+        bm.rhs, feq_dev, (const long long*)a_dev, (const long long*)b_dev, (const long long*)dst_dev, sign, count);
+    s->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(-(int)e, "lbm_sim_rhs_update", cudaGetErrorString(e));
+    return 0;
+}
+
+// Small host block -> device rows on the simulation's stream without stalling the host: the rows go
+// through one of two page-locked staging buffers (the host waits only for the copy that used the same
+// buffer two uploads ago), so the caller may overwrite `src` as soon as the call returns.
+extern "C" int lbm_sim_upload_rows(lbm_sim* s, void* dst_dev, uint64_t dpitch, const void* src_host, uint64_t spitch,
+                                   uint64_t width, uint64_t height) {
+    if (!s || !dst_dev || !src_host) return ARG_ERROR("lbm_sim_upload_rows: null argument");
+    if (width == 0 || height == 0) return 0;
+    if (width > spitch || width > dpitch) return ARG_ERROR("lbm_sim_upload_rows: width exceeds a pitch");
+    const uint64_t bytes = width * height;
+    const int b = s->up_next;
+    s->up_next ^= 1;
+    if (s->up_event[b]) CUDA_TRY(cudaEventSynchronize(s->up_event[b]));
+    else CUDA_TRY(cudaEventCreateWithFlags(&s->up_event[b], cudaEventDisableTiming));
+    if (bytes > s->up_bytes[b]) {
+        if (s->up_buf[b]) cudaFreeHost(s->up_buf[b]);
+        s->up_buf[b] = nullptr;
+        s->up_bytes[b] = 0;
+        CUDA_TRY(cudaMallocHost(&s->up_buf[b], bytes));
+        s->up_bytes[b] = bytes;
+    }
+    for (uint64_t r = 0; r < height; ++r)
+        memcpy((char*)s->up_buf[b] + r * width, (const char*)src_host + r * spitch, width);
+    CUDA_TRY(cudaMemcpy2DAsync(dst_dev, dpitch, s->up_buf[b], width, width, height, cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaEventRecord(s->up_event[b], s->stream));
     return 0;
 }
 

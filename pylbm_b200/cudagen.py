@@ -389,39 +389,44 @@ _GUARD_PLAIN = "    if (i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]) return;
 # entry stores, so the input array alone determines every value.
 _GUARD_TASKS = r"""    const bool active_ = !(i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]);
     if (!TASKS && !active_) return;
-    unsigned long long tmask_ = 0ull;
+    // the task range of this block is requested first and consumed after the population loads have
+    // been issued, so that the two memory round trips overlap
+    int t0_ = 0, t1_ = 0;
+    if (TASKS) {
+        const long long bid_ = ((long long)(i0 - g.w[0]) * tasks.ngroups_y + by) * tasks.ngroups_x + blockIdx.x;
+        t0_ = __ldg(tasks.block_ptr + bid_);
+        t1_ = __ldg(tasks.block_ptr + bid_ + 1);
+    }"""
+
+_TASKS_CHAIN = r"""    unsigned long long tmask_ = 0ull;
     extern __shared__ __align__(16) unsigned char lbmk_smem_[];
     real_c* const sm_val_ = (real_c*)lbmk_smem_;                                  // [NQ][LBMK_BLOCK]
     unsigned long long* const sm_mask_ = (unsigned long long*)(sm_val_ + NQ_ * LBMK_BLOCK);
-    if (TASKS) {
-        const long long bid_ = ((long long)(i0 - g.w[0]) * tasks.ngroups_y + by) * tasks.ngroups_x + blockIdx.x;
-        const int t0_ = __ldg(tasks.block_ptr + bid_), t1_ = __ldg(tasks.block_ptr + bid_ + 1);
-        if (t1_ > t0_) {                                   // block-uniform
-            sm_mask_[tid] = 0ull;
-            __syncthreads();
-            for (int t = t0_ + (int)tid; t < t1_; t += LBMK_BLOCK) {
-                const unsigned code = __ldg(tasks.code + t);
-                const unsigned kind = code >> 16, kk = (code >> 8) & 255u, th = code & 255u;
-                const double a = (double)__ldg(fin + __ldg(tasks.l0 + t));
-                double v = a;                                                  // Neumann
-                if (kind != 4u) {
-                    const double r = __ldg(tasks.rhs[t]);
-                    if (kind == 0u) v = __dadd_rn(a, r);                       // bounce-back
-                    else if (kind == 1u) v = __dadd_rn(-a, r);                 // anti-bounce-back
-                    else {
-                        const double b = (double)__ldg(fin + __ldg(tasks.l1 + t));
-                        const double d = __ldg(tasks.dist + t);
-                        const double far = __dmul_rn(__dsub_rn(1.0, d), b);
-                        const double near = __dmul_rn(d, a);
-                        v = __dadd_rn(__dadd_rn(far, kind == 2u ? near : -near), r);   // Bouzidi (anti-)bounce-back
-                    }
-                }
-                sm_val_[kk * LBMK_BLOCK + th] = (real_c)(%(tin)s)v;       // rounded like the stored value
-                atomicOr(sm_mask_ + th, 1ull << kk);
+    if (TASKS && t1_ > t0_) {                              // block-uniform
+        sm_mask_[tid] = 0ull;
+        __syncthreads();
+        for (int t = t0_ + (int)tid; t < t1_; t += LBMK_BLOCK) {
+            const unsigned code = __ldg(tasks.code + t);
+            const long long l0_ = __ldg(tasks.l0 + t), l1_ = __ldg(tasks.l1 + t);
+            const double* const rp_ = tasks.rhs[t];
+            const double d = __ldg(tasks.dist + t);
+            const unsigned kind = code >> 16, kk = (code >> 8) & 255u, th = code & 255u;
+            const double a = (double)__ldg(fin + l0_);
+            const double b = (double)__ldg(fin + l1_);     // (position 0 when the kind has one load)
+            const double r = rp_ ? __ldg(rp_) : 0.0;
+            double v = a;                                                      // Neumann
+            if (kind == 0u) v = __dadd_rn(a, r);                               // bounce-back
+            else if (kind == 1u) v = __dadd_rn(-a, r);                         // anti-bounce-back
+            else if (kind != 4u) {
+                const double far = __dmul_rn(__dsub_rn(1.0, d), b);
+                const double near = __dmul_rn(d, a);
+                v = __dadd_rn(__dadd_rn(far, kind == 2u ? near : -near), r);   // Bouzidi (anti-)bounce-back
             }
-            __syncthreads();
-            tmask_ = sm_mask_[tid];
+            sm_val_[kk * LBMK_BLOCK + th] = (real_c)(%(tin)s)v;           // rounded like the stored value
+            atomicOr(sm_mask_ + th, 1ull << kk);
         }
+        __syncthreads();
+        tmask_ = sm_mask_[tid];
     }
     if (active_) {"""
 
@@ -540,16 +545,25 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
     tin = "real_m" if ir.in_array == "m" else "real_f"
     tout = "real_m" if ir.out_array == "m" else "real_f"
     loads = []
-    for k, sym in enumerate(ir.in_syms):
-        loads.append("    %sreal_c %s = (real_c)__ldg((const %s*)(pin + offs.in[%d]));"
-                     % ("" if images else "const ", sym, tin, k))
     overrides = ""
     if images:
-        lines = ["    if (TASKS && tmask_) {   // pulled values that are boundary entries of this step"]
+        # raw loads first (no conversion: nothing consumes them before the task chain has been issued)
+        loads.append("    %s %s;" % (tin, ", ".join("r%d_ = 0" % k for k in range(nq))))
+        loads.append("    if (active_) {")
+        for k in range(nq):
+            loads.append("        r%d_ = __ldg((const %s*)(pin + offs.in[%d]));" % (k, tin, k))
+        loads.append("    }")
+        lines = [_TASKS_CHAIN % dict(tin=tin)]
+        for k, sym in enumerate(ir.in_syms):
+            lines.append("    real_c %s = (real_c)r%d_;" % (sym, k))
+        lines.append("    if (TASKS && tmask_) {   // pulled values that are boundary entries of this step")
         for k, sym in enumerate(ir.in_syms):
             lines.append("        if (tmask_ & (1ull << %d)) %s = sm_val_[%d * LBMK_BLOCK + tid];" % (k, sym, k))
         lines.append("    }")
         overrides = "\n".join(lines)
+    else:
+        for k, sym in enumerate(ir.in_syms):
+            loads.append("    const real_c %s = (real_c)__ldg((const %s*)(pin + offs.in[%d]));" % (sym, tin, k))
     body = ["    const real_c %s = %s;" % (lhs, pr.doprint(rhs)) for lhs, rhs in temps]
     if images:
         vels = [tuple(-o for o in _canonical(off)) for off in ir.in_offsets]
@@ -587,7 +601,7 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         template="template <bool WALLZ, bool TASKS>\n" if images else "",
         peer_param=(", const lbmk_peers pr, const lbmk_images img, const lbmk_walls walls, const lbmk_tasks tasks"
                     if images else ""),
-        guard=(_GUARD_TASKS % dict(tin=tin)) if images else _GUARD_PLAIN,
+        guard=_GUARD_TASKS if images else _GUARD_PLAIN,
         guard_end="    }" if images else "",
         overrides=overrides,
         images_launch=(_IMAGES_LAUNCH % dict(nout=len(outs), tout=tout, sym_table=sym_table)) if images else "",

@@ -305,6 +305,9 @@ class CudaEngine:
                 ptr(tasks["ibc"]), ptr(tasks["entry"]), tasks["ngroups_y"], tasks["ngroups_x"], tasks["tx"]),
                 "lbm_sim_set_tasks")
         self.bc.tasks = None if tasks is None else {k: tasks[k] for k in ("ntasks", "nentries", "nblocks")}
+        if not os.environ.get("PYLBM_B200_HOST_TIME_BC"):
+            for method in self.bc.methods:
+                method.prepare_time_bc(self)
         self._time_dependent = any(m.is_time_dependent for m in self.bc.methods)
         self._need_init = False
 
@@ -543,7 +546,11 @@ class CudaEngine:
 
     def _update_time_bc(self):
         for method in self.bc.methods:
-            if method.is_time_dependent:
+            if not method.is_time_dependent:
+                continue
+            if getattr(method, "_time_plans", None):
+                method.update_feq_device(self)      # only the user's callback runs on the host
+            else:
                 method.update_feq(self)
                 method.set_rhs()
                 method.push_rhs(self._handle)

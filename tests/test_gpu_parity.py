@@ -359,3 +359,31 @@ def test_boundary_entries_in_the_fused_kernel_are_bit_identical_to_the_list_kern
     assert np.array_equal(Fa[:, fluid], Fb[:, fluid])
     for key in a.scheme.consm:
         assert np.array_equal(a.m[key][fluid], b.m[key][fluid])
+
+
+def test_time_dependent_boundary_values_on_the_device(monkeypatch):
+    """time_bc labels (reference: boundary.py:307-321): the device path (asynchronous upload of the
+    callback's moments, equilibrium + m2f + rhs recomputation enqueued on the simulation's stream, no
+    synchronisation) gives the populations of the host path (NumPy set_rhs + synchronous upload) bit for
+    bit, with the task table and with the list kernels."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    def run(host, tasks):
+        if host:
+            monkeypatch.setenv("PYLBM_B200_HOST_TIME_BC", "1")
+        else:
+            monkeypatch.delenv("PYLBM_B200_HOST_TIME_BC", raising=False)
+        monkeypatch.setenv("PYLBM_B200_TASKS", "1" if tasks else "0")
+        sim = pylbm_b200.Simulation(cases.rayleigh_benard(nx=64, ny=32, period=0.05, perturb=0))
+        assert sim._time_dependent
+        assert any(getattr(m, "_time_plans", None) for m in sim.bc.methods) == (not host)
+        for _ in range(12):
+            sim.one_time_step()
+        sim.boundary_condition()
+        sim.run(9)
+        return sim.container.F.get()[:, 1:-1, 1:-1]
+
+    ref = run(True, False)
+    assert np.array_equal(run(False, False), ref)
+    assert np.array_equal(run(False, True), ref)
