@@ -251,6 +251,9 @@ struct lbmk_offs_%(name)s {
     unsigned fold;   // 0: blockIdx.y / blockIdx.z are the row group / the index of axis 0; otherwise the
                      // number of row groups per axis-0 index, (z, y) being one linear index (more than
                      // 65535 row groups or planes: e.g. a 2-D lattice with 100 000 rows)
+    unsigned pair;   // a thread that computes several cells takes them along axis 0 (0) or from consecutive
+                     // row groups of axis 1 (1: lattices with a single plane)
+    unsigned vgy;    // row groups per plane of the lattice (the grid has fewer when pair == 1)
 };
 
 %(template)s__global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
@@ -272,23 +275,10 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
         bz = (unsigned)(lin / offs.fold);
         by = (unsigned)(lin - (unsigned long long)bz * offs.fold);
     }
-    const int i1 = g.lo[1] + (int)(by * ty + (tid >> txshift));
-    const int i0 = g.lo[0] + (int)bz;
-%(guard)s
     const long long rowstride = g.pitch;
     const long long planestride = (long long)g.n[1] * g.pitch;
-    const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
     (void)rowstride; (void)planestride;
-    unsigned long long pin = (unsigned long long)(fin + cell);
-    unsigned long long pout = (unsigned long long)(fout + cell);
-    asm volatile("" : "+l"(pin), "+l"(pout));   // keep `pointer + constant-bank offset` as the address form
-%(loads)s
-%(overrides)s
-%(prologue)s
-%(body)s
-%(stores)s
-%(images)s
-%(guard_end)s
+%(thread_body)s
 }
 
 %(launch_head)s
@@ -301,6 +291,10 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
     static const int noff[%(nin)d][3] = {%(offset_table)s};
     lbmk_offs_%(name)s offs;
     offs.fold = 0;
+    offs.vgy = grid.y;
+    offs.pair = (n0 > 1) ? 0u : 1u;
+    if (offs.pair == 0u) grid.z = (grid.z + %(cpt)d - 1) / %(cpt)d;
+    else grid.y = (grid.y + %(cpt)d - 1) / %(cpt)d;
     if (grid.y > 65535u || grid.z > 65535u) {
         // (row group, plane) as one linear index spread over (y, z)
         const unsigned long long total = (unsigned long long)grid.y * grid.z;
@@ -378,7 +372,16 @@ _IMAGES_LAUNCH = r"""
 """
 
 
-_GUARD_PLAIN = "    if (i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]) return;"
+_THREAD_PLAIN = r"""    const int i1 = g.lo[1] + (int)(by * ty + (tid >> txshift));
+    const int i0 = g.lo[0] + (int)bz;
+    if (i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]) return;
+    const long long cell = g.lead + (long long)i0 * planestride + (long long)i1 * rowstride + i2;
+    unsigned long long pin = (unsigned long long)(fin + cell);
+    unsigned long long pout = (unsigned long long)(fout + cell);
+    asm volatile("" : "+l"(pin), "+l"(pout));   // keep `pointer + constant-bank offset` as the address form
+%(loads)s
+%(body)s
+%(stores)s"""
 
 # Boundary entries folded into the fused kernel (TASKS instantiation).  Entry `f_k(c_out) = value` of a
 # boundary method is read by exactly one pull: cell c_out + v_k, population k.  Instead of a list kernel
@@ -387,21 +390,40 @@ _GUARD_PLAIN = "    if (i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]) return;
 # round-to-nearest arithmetic as the list kernel k_bc (runtime) -- and hands the values to the owning
 # threads through shared memory.  The host (boundary.plan_tasks) proves that no entry reads what another
 # entry stores, so the input array alone determines every value.
-_GUARD_TASKS = r"""    const bool active_ = !(i2 >= g.hi[2] || i1 >= g.hi[1] || i0 >= g.hi[0]);
-    if (!TASKS && !active_) return;
-    // the task range of this block is requested first and consumed after the population loads have
-    // been issued, so that the two memory round trips overlap
-    int t0_ = 0, t1_ = 0;
-    if (TASKS) {
-        const long long bid_ = ((long long)(i0 - g.w[0]) * tasks.ngroups_y + by) * tasks.ngroups_x + blockIdx.x;
-        t0_ = __ldg(tasks.block_ptr + bid_);
-        t1_ = __ldg(tasks.block_ptr + bid_ + 1);
+#
+# A thread computes CPT cells (1 for fp64 populations, 2 for fp32 populations: half the bytes per load,
+# so twice the loads must be in flight to keep HBM busy at the same occupancy).  Coordinates and the
+# loads of ALL its cells come first, then the cells are computed one after the other.
+_CELL_COORDS = r"""    // ---- cell %(c)d of this thread
+    const unsigned by%(c)d_ = offs.pair ? by * %(cpt)du + %(c)du : by;
+    const unsigned bz%(c)d_ = offs.pair ? bz : bz * %(cpt)du + %(c)du;
+    const int i1_%(c)d = g.lo[1] + (int)(by%(c)d_ * ty + (tid >> txshift));
+    const int i0_%(c)d = g.lo[0] + (int)bz%(c)d_;
+    const bool act%(c)d_ = !(i2 >= g.hi[2] || i1_%(c)d >= g.hi[1] || i0_%(c)d >= g.hi[0]);
+    const long long cell%(c)d_ = g.lead + (long long)i0_%(c)d * planestride + (long long)i1_%(c)d * rowstride + i2;
+    // the task range of the block is requested first and consumed after the population loads have
+    // been issued, so that the memory round trips overlap
+    int ta%(c)d_ = 0, tb%(c)d_ = 0;
+    if (TASKS && i0_%(c)d < g.hi[0] && by%(c)d_ < offs.vgy) {
+        const long long bid_ = ((long long)(i0_%(c)d - g.w[0]) * tasks.ngroups_y + by%(c)d_) * tasks.ngroups_x + blockIdx.x;
+        ta%(c)d_ = __ldg(tasks.block_ptr + bid_);
+        tb%(c)d_ = __ldg(tasks.block_ptr + bid_ + 1);
     }"""
 
-_TASKS_CHAIN = r"""    unsigned long long tmask_ = 0ull;
-    extern __shared__ __align__(16) unsigned char lbmk_smem_[];
+_CELL_OPEN = r"""    {   // ======== cell %(c)d ========
+    const int i0 = i0_%(c)d, i1 = i1_%(c)d;
+    const bool active_ = act%(c)d_;
+    const long long cell = cell%(c)d_;
+    const int t0_ = ta%(c)d_, t1_ = tb%(c)d_;
+    unsigned long long pout = (unsigned long long)(fout + cell);
+    asm volatile("" : "+l"(pout));
+    (void)i0; (void)i1;"""
+
+_SMEM_DECL = r"""    extern __shared__ __align__(16) unsigned char lbmk_smem_[];
     real_c* const sm_val_ = (real_c*)lbmk_smem_;                                  // [NQ][LBMK_BLOCK]
-    unsigned long long* const sm_mask_ = (unsigned long long*)(sm_val_ + NQ_ * LBMK_BLOCK);
+    unsigned long long* const sm_mask_ = (unsigned long long*)(sm_val_ + NQ_ * LBMK_BLOCK);"""
+
+_TASKS_CHAIN = r"""    unsigned long long tmask_ = 0ull;
     if (TASKS && t1_ > t0_) {                              // block-uniform
         sm_mask_[tid] = 0ull;
         __syncthreads();
@@ -519,7 +541,7 @@ _CALL_WALLS = """    const lbmk_peers pr_ = peers ? *peers : lbmk_peers{nullptr,
     if (tasks) {
         // the table maps cells to (block, thread) of THIS launch geometry
         if (walls || tasks->tx != g->tx || g->lo[1] != g->w[1] || g->lo[2] != g->w[2] || offs.fold
-            || tasks->ngroups_x != (int)grid.x || tasks->ngroups_y != (int)grid.y) return -4;
+            || tasks->ngroups_x != (int)grid.x || tasks->ngroups_y != (int)offs.vgy) return -4;
         const size_t smem_ = (size_t)%(nin)d * LBMK_BLOCK * sizeof(real_c_%(name)s) + LBMK_BLOCK * sizeof(unsigned long long);
         static bool attr_ = false;
         if (!attr_ && smem_ > 48 * 1024) {
@@ -536,47 +558,65 @@ _CALL_WALLS = """    const lbmk_peers pr_ = peers ? *peers : lbmk_peers{nullptr,
             (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, lbmk_walls{}, notasks_%(scalar_args)s);"""
 
 
-def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0, compute="double"):
+def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0, compute="double", cpt=1):
     """CUDA source of one per-cell kernel + its C-ABI launcher.  `compute` is the arithmetic type of
-    the kernel body (double, or float for the all-fp32 mode of the fused kernel)."""
+    the kernel body (double, or float for the all-fp32 mode of the fused kernel); `cpt` the number of
+    cells a thread of the fused kernel computes."""
     temps, outs = lower_statements(ir.statements, ir.outputs, cse=cse)
     pr = _printers[compute == "float"]
     nq = len(ir.in_syms)
     tin = "real_m" if ir.in_array == "m" else "real_f"
     tout = "real_m" if ir.out_array == "m" else "real_f"
-    loads = []
-    overrides = ""
-    if images:
-        # raw loads first (no conversion: nothing consumes them before the task chain has been issued)
-        loads.append("    %s %s;" % (tin, ", ".join("r%d_ = 0" % k for k in range(nq))))
-        loads.append("    if (active_) {")
-        for k in range(nq):
-            loads.append("        r%d_ = __ldg((const %s*)(pin + offs.in[%d]));" % (k, tin, k))
-        loads.append("    }")
-        lines = [_TASKS_CHAIN % dict(tin=tin)]
-        for k, sym in enumerate(ir.in_syms):
-            lines.append("    real_c %s = (real_c)r%d_;" % (sym, k))
-        lines.append("    if (TASKS && tmask_) {   // pulled values that are boundary entries of this step")
-        for k, sym in enumerate(ir.in_syms):
-            lines.append("        if (tmask_ & (1ull << %d)) %s = sm_val_[%d * LBMK_BLOCK + tid];" % (k, sym, k))
-        lines.append("    }")
-        overrides = "\n".join(lines)
-    else:
-        for k, sym in enumerate(ir.in_syms):
-            loads.append("    const real_c %s = (real_c)__ldg((const %s*)(pin + offs.in[%d]));" % (sym, tin, k))
+    if not images:
+        cpt = 1
     body = ["    const real_c %s = %s;" % (lhs, pr.doprint(rhs)) for lhs, rhs in temps]
+    vels = [tuple(-o for o in _canonical(off)) for off in ir.in_offsets]
     if images:
-        vels = [tuple(-o for o in _canonical(off)) for off in ir.in_offsets]
         stores = [
             "    { const %s o_ = (%s)(%s); %s* p_ = (%s*)(pout + offs.out[%d]); __stcg(p_, o_);%s }"
             % (tout, tout, pr.doprint(o), tout, tout, k, _inline_image(vels[k], k, slab, tout))
             for k, o in enumerate(outs)
         ]
+        parts = [_SMEM_DECL]
+        for c in range(cpt):
+            parts.append(_CELL_COORDS % dict(c=c, cpt=cpt))
+        # a cell beyond the range has every later cell of the thread beyond it too
+        parts.append("    if (!TASKS && !act0_) return;")
+        # raw loads of all cells first (no conversion: nothing consumes them before the task chains and
+        # the loads of the other cells have been issued)
+        for c in range(cpt):
+            parts.append("    %s %s;" % (tin, ", ".join("r%d_%d = 0" % (c, k) for k in range(nq))))
+            parts.append("    if (act%d_) {" % c)
+            parts.append("        unsigned long long pin = (unsigned long long)(fin + cell%d_);" % c)
+            parts.append('        asm volatile("" : "+l"(pin));   // keep `pointer + constant-bank offset` as the address form')
+            for k in range(nq):
+                parts.append("        r%d_%d = __ldg((const %s*)(pin + offs.in[%d]));" % (c, k, tin, k))
+            parts.append("    }")
+        images_tail = _images_code(vels, tout, slab)
+        for c in range(cpt):
+            parts.append(_CELL_OPEN % dict(c=c))
+            parts.append(_TASKS_CHAIN % dict(tin=tin))
+            for k, sym in enumerate(ir.in_syms):
+                parts.append("    real_c %s = (real_c)r%d_%d;" % (sym, c, k))
+            parts.append("    if (TASKS && tmask_) {   // pulled values that are boundary entries of this step")
+            for k, sym in enumerate(ir.in_syms):
+                parts.append("        if (tmask_ & (1ull << %d)) %s = sm_val_[%d * LBMK_BLOCK + tid];" % (k, sym, k))
+            parts.append("    }")
+            parts.append(_IMAGES_PROLOGUE % dict(tout=tout))
+            parts.extend(body)
+            parts.extend(stores)
+            parts.append(images_tail)
+            parts.append("    }   // active_")
+            parts.append("    }   // cell %d" % c)
+        thread_body = "\n".join(parts)
     else:
+        loads = ["    const real_c %s = (real_c)__ldg((const %s*)(pin + offs.in[%d]));" % (sym, tin, k)
+                 for k, sym in enumerate(ir.in_syms)]
         stores = [
             "    __stcg((%s*)(pout + offs.out[%d]), (%s)(%s));" % (tout, k, tout, pr.doprint(o))
             for k, o in enumerate(outs)
         ]
+        thread_body = _THREAD_PLAIN % dict(loads="\n".join(loads), body="\n".join(body), stores="\n".join(stores))
     add, mul, div = count_ops(temps, outs)
     scal_params = "".join(", const real_c_%s %s" % (ir.name, _c_name(s)) for s in ir.scalars)
     scal_args = "".join(", (real_c_%s)scalars[%d]" % (ir.name, i) for i in range(len(ir.scalars)))
@@ -590,36 +630,31 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         tc=compute,
         nin=nq,
         nout=len(outs),
-        ops="%d add, %d mul, %d div before FMA contraction, %s arithmetic" % (add, mul, div, compute),
+        cpt=cpt,
+        ops="%d add, %d mul, %d div before FMA contraction, %s arithmetic, %d cell(s) per thread"
+            % (add, mul, div, compute, cpt),
         minblocks=minblocks,
         scalar_params=scal_params,
         scalar_args=scal_args,
         offset_table=table,
-        loads="\n".join(loads),
-        images=_images_code([tuple(-o for o in _canonical(off)) for off in ir.in_offsets], tout, slab) if images else "",
-        prologue=(_IMAGES_PROLOGUE % dict(tout=tout)) if images else "",
+        thread_body=thread_body,
         template="template <bool WALLZ, bool TASKS>\n" if images else "",
         peer_param=(", const lbmk_peers pr, const lbmk_images img, const lbmk_walls walls, const lbmk_tasks tasks"
                     if images else ""),
-        guard=_GUARD_TASKS if images else _GUARD_PLAIN,
-        guard_end="    }" if images else "",
-        overrides=overrides,
         images_launch=(_IMAGES_LAUNCH % dict(nout=len(outs), tout=tout, sym_table=sym_table)) if images else "",
         kernel_call=(_CALL_WALLS if images else _CALL_PLAIN) % dict(name=ir.name, tin=tin, tout=tout,
                                                                     scalar_args=scal_args, nin=nq),
         launch_head=(_LAUNCH_HEAD_WALLS if images else _LAUNCH_HEAD) % dict(name=ir.name),
         launch_tail=(_LAUNCH_TAIL_WALLS % dict(name=ir.name)) if images else "",
-        body="\n".join(body),
-        stores="\n".join(stores),
     )
     # user symbols may not be valid C identifiers (e.g. `lambda`)
-    for s in ir.scalars:
-        if _c_name(s) != s:
-            src = _rename_identifier(src, s, _c_name(s))
+    for s_ in ir.scalars:
+        if _c_name(s_) != s_:
+            src = _rename_identifier(src, s_, _c_name(s_))
     return src, (add, mul, div)
 
 
-_C_KEYWORDS = {"tasks", "active_", "tmask_", "lambda", "double", "int", "float", "long", "short", "register", "const", "void", "auto", "g", "fin", "fout", "cell", "tid",
+_C_KEYWORDS = {"tasks", "lambda", "double", "int", "float", "long", "short", "register", "const", "void", "auto", "g", "fin", "fout", "cell", "tid",
                "pin", "pout", "offs", "pr", "tx", "ty", "i0", "i1", "i2", "d0", "d1", "d2", "real_c"}
 
 
@@ -646,7 +681,20 @@ extern "C" const char* lbmk_describe(void)
 """
 
 
-def default_minblocks(nv, compute="double"):
+def default_cpt(storage):
+    """cells per thread of the fused kernel: 2 with fp32 populations (a load brings half the bytes, so
+    twice as many must be in flight: ncu of the fp32-storage kernel with one cell per thread showed no
+    saturated pipe -- fp64 57 %%, conversions (XU) 29 %%, issue 61 %% -- and 64 %% of the DRAM bandwidth at
+    20 resident warps per SM), 1 with fp64 populations (at the roofline already).  PYLBM_B200_CPT overrides."""
+    import os
+
+    env = os.environ.get("PYLBM_B200_CPT")
+    if env:
+        return max(1, min(4, int(env)))
+    return 2 if storage == "float" else 1
+
+
+def default_minblocks(nv, compute="double", cpt=1):
     """resident 128-thread blocks per SM requested through __launch_bounds__ for the fused
     kernel (caps registers: 65536 / (128 * minblocks)); tuned on B200, see DESIGN.md:
     fp64 arithmetic 5 (<= 102 registers; 6 spills), fp32 arithmetic 8 (56 registers; 5 -> 8 gave
@@ -656,6 +704,8 @@ def default_minblocks(nv, compute="double"):
     env = os.environ.get("PYLBM_B200_MINBLOCKS")
     if env:
         return int(env)
+    if cpt > 1:          # the raw loads of the other cells stay live while one cell is computed
+        return 6 if compute == "float" else 4
     return 8 if compute == "float" else 5
 
 
@@ -668,7 +718,8 @@ def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):
     h = hashlib.sha256()
     with open(__file__.replace(".pyc", ".py"), "rb") as fh:
         h.update(fh.read())
-    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv, compute), compute)).encode())
+    cpt = default_cpt(storage)
+    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv, compute, cpt), compute, cpt)).encode())
     for ir in kernels:
         h.update(repr((ir.name, ir.in_array, ir.out_array, bool(ir.inner), list(ir.scalars),
                        [str(s) for s in ir.in_syms], [tuple(o) for o in ir.in_offsets])).encode())
@@ -692,11 +743,13 @@ def generate_source(kernels, dim, nv, storage="double", cse=True, compute="doubl
 
     parts = [_HEADER % dict(abi=ABI_VERSION, storage=storage, slab=3 - dim)]
     info = {"abi": ABI_VERSION, "dim": dim, "nv": nv, "storage": storage, "compute": compute, "routines": {}}
+    cpt = default_cpt(storage)
     for ir in kernels:
         fused = ir.name == "one_time_step"
         src, ops = kernel_source(ir, storage=storage, cse=cse, images=fused,
-                                 minblocks=default_minblocks(nv, compute) if fused else 1, slab=3 - dim,
-                                 compute=compute if ir.name in ("one_time_step", "transport") else "double")
+                                 minblocks=default_minblocks(nv, compute, cpt) if fused else 1, slab=3 - dim,
+                                 compute=compute if ir.name in ("one_time_step", "transport") else "double",
+                                 cpt=cpt)
         parts.append(src)
         info["routines"][ir.name] = {
             "scalars": list(ir.scalars),

@@ -313,20 +313,18 @@ class CudaEngine:
 
     def _plan_tasks(self):
         """boundary entries evaluated by the fused kernel itself (boundary.plan_tasks): one launch per
-        step.  Chosen for lattices where the list kernels are a visible share of the step -- small
-        lattices (launch-bound) and lattices with few entries per cell; big wall-dominated boxes keep the
-        list kernels / the fused walls (measured).  PYLBM_B200_TASKS=0/1 forces it off / on."""
+        step instead of list kernels + fused kernel.  OPT-IN (PYLBM_B200_TASKS=1): measured on B200 it
+        loses everywhere -- the entries of a block need three dependent memory round trips (task range,
+        task records, populations) before the block can start its collision, which costs more than the
+        list kernels it removes (D2Q9 256^2: 7.2 vs 5.1 us/step; Karman 4096x1024: 103.0 vs 100.5 us;
+        D3Q19 256^3: 1.10 vs 0.82 ms; profiles/r02_tasks_vs_lists.md).  Kept because it is bit-identical
+        and tested, and because it makes a step a single launch (useful under a debugger / ncu)."""
         from .boundary import plan_tasks
 
         self.bc.walls = None
-        mode = os.environ.get("PYLBM_B200_TASKS", "auto")
-        if mode == "0" or not self.bc.methods:
+        if os.environ.get("PYLBM_B200_TASKS", "0") != "1" or not self.bc.methods:
             return None
         F = self.container.F
-        cells = float(np.prod(self.domain.shape_in))
-        nentries = sum(len(m._keep[0]) for m in self.bc.methods)
-        if mode != "1" and not (cells <= 2 ** 22 or nentries <= 0.03 * cells):
-            return None
         info = []
         for method in self.bc.methods:
             store, l0, l1, _, dist, level_ptr, two_phase = method._keep
