@@ -233,6 +233,17 @@ typedef struct {       // boundary entries evaluated by the pulling thread (see 
 #define SLAB %(slab)d
 
 typedef %(storage)s real_f;   // storage type of the populations in HBM
+// fp32 -> fp64 on the integer pipe (exact for normal numbers: rebias the exponent, widen the mantissa);
+// zero, subnormals, inf and nan take the conversion instruction.  Experiment: PYLBM_B200_F2D=int.
+__device__ __forceinline__ double lbmk_f2d(float x) {
+    const unsigned u = __float_as_uint(x);
+    const unsigned e = (u >> 23) & 0xffu;
+    const unsigned hi = (u & 0x80000000u) | (((u & 0x7fffffffu) >> 3) + 0x38000000u);
+    double d = __hiloint2double((int)hi, (int)(u << 29));
+    if (e == 0u || e == 255u) d = (double)x;
+    return d;
+}
+__device__ __forceinline__ double lbmk_f2d(double x) { return x; }
 typedef double real_m;        // moments are always stored in fp64
 #define LBMK_BLOCK 128
 """
@@ -596,8 +607,12 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         for c in range(cpt):
             parts.append(_CELL_OPEN % dict(c=c))
             parts.append(_TASKS_CHAIN % dict(tin=tin))
+            import os
+
+            intconv = os.environ.get("PYLBM_B200_F2D") == "int" and compute == "double"
             for k, sym in enumerate(ir.in_syms):
-                parts.append("    real_c %s = (real_c)r%d_%d;" % (sym, c, k))
+                parts.append("    real_c %s = %sr%d_%d%s;" % (sym, "lbmk_f2d(" if intconv else "(real_c)", c, k,
+                                                              ")" if intconv else ""))
             parts.append("    if (TASKS && tmask_) {   // pulled values that are boundary entries of this step")
             for k, sym in enumerate(ir.in_syms):
                 parts.append("        if (tmask_ & (1ull << %d)) %s = sm_val_[%d * LBMK_BLOCK + tid];" % (k, sym, k))
@@ -682,16 +697,17 @@ extern "C" const char* lbmk_describe(void)
 
 
 def default_cpt(storage):
-    """cells per thread of the fused kernel: 2 with fp32 populations (a load brings half the bytes, so
-    twice as many must be in flight: ncu of the fp32-storage kernel with one cell per thread showed no
-    saturated pipe -- fp64 57 %%, conversions (XU) 29 %%, issue 61 %% -- and 64 %% of the DRAM bandwidth at
-    20 resident warps per SM), 1 with fp64 populations (at the roofline already).  PYLBM_B200_CPT overrides."""
+    """cells per thread of the fused kernel.  1: measured on B200 (D3Q19 512^3, profiles/r02_fp32_modes.md) two
+    cells per thread -- twice the loads in flight per thread, but 128 registers, 16 resident warps -- is
+    SLOWER with fp32 populations and fp64 arithmetic (0.62 vs 0.77 of the roofline: that kernel is bound by
+    warp-level parallelism for its fp64 / conversion chains, not by bytes in flight) and within noise for
+    the all-fp32 kernel (0.924 vs 0.916).  PYLBM_B200_CPT=2 builds the two-cell variant."""
     import os
 
     env = os.environ.get("PYLBM_B200_CPT")
     if env:
         return max(1, min(4, int(env)))
-    return 2 if storage == "float" else 1
+    return 1
 
 
 def default_minblocks(nv, compute="double", cpt=1):
@@ -718,8 +734,11 @@ def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):
     h = hashlib.sha256()
     with open(__file__.replace(".pyc", ".py"), "rb") as fh:
         h.update(fh.read())
+    import os
+
     cpt = default_cpt(storage)
-    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv, compute, cpt), compute, cpt)).encode())
+    h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv, compute, cpt), compute, cpt,
+                   os.environ.get("PYLBM_B200_F2D", ""))).encode())
     for ir in kernels:
         h.update(repr((ir.name, ir.in_array, ir.out_array, bool(ir.inner), list(ir.scalars),
                        [str(s) for s in ir.in_syms], [tuple(o) for o in ir.in_offsets])).encode())
