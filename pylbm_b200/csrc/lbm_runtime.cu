@@ -16,6 +16,7 @@
 #include <sys/syscall.h>
 #include <unistd.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -490,6 +491,9 @@ static int nccl_load() {
     return 0;
 }
 
+struct CommEntry { nccl_comm comm; int rank, nranks; };
+static std::map<std::string, CommEntry> g_comms;
+
 #define NCCL_TRY(call)                                                                  \
     do {                                                                                \
         int r_ = (call);                                                                \
@@ -711,7 +715,7 @@ extern "C" void lbm_sim_destroy(lbm_sim* s) {
     }
     cudaFree(s->flags);
     if (s->wait_err) cudaFreeHost(s->wait_err);
-    if (s->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(s->comm);
+    // (communicators are shared between the time-step objects of a process and live as long as it does)
     free_tasks(s);
     for (int i = 0; i < 2; ++i) {
         if (s->up_buf[i]) cudaFreeHost(s->up_buf[i]);
@@ -1390,9 +1394,21 @@ extern "C" int lbm_sim_comm_init(lbm_sim* s, int rank, int nranks, const void* i
     if (!id128) return ARG_ERROR("null unique id");
     int rc = nccl_load();
     if (rc) return rc;
-    nccl_uid id;
-    memcpy(&id, id128, 128);
-    NCCL_TRY(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
+    // One communicator per unique id and process, kept for the life of the process: an ncclUniqueId can
+    // bootstrap only one communicator, and a process builds several time-step objects over the same
+    // ranks one after the other (bench.py: parity cases, the headline workload, the other configurations).
+    const std::string key((const char*)id128, 128);
+    auto it = g_comms.find(key);
+    if (it != g_comms.end()) {
+        if (it->second.rank != rank || it->second.nranks != nranks)
+            return ARG_ERROR("lbm_sim_comm_init: this unique id already belongs to a communicator of another shape");
+        s->comm = it->second.comm;
+    } else {
+        nccl_uid id;
+        memcpy(&id, id128, 128);
+        NCCL_TRY(g_nccl.CommInitRank(&s->comm, nranks, id, rank));
+        g_comms[key] = CommEntry{s->comm, rank, nranks};
+    }
     if (getenv("PYLBM_B200_NO_OVERLAP")) s->overlap = 0;   // debugging aid: exchange on the compute stream
     s->wrap_mask &= ~(1 << s->slab_axis);   // the slab axis is exchanged between ranks, not wrapped
     s->ghost_fresh = 0;

@@ -1,8 +1,10 @@
 #!/usr/bin/env bash
 # 2-GPU batch: multi-GPU tests, bench with the parity block (peer and NCCL halos)
 mkdir -p gpurun_out
+if [ -z "$SKIP_TESTS" ]; then
 python -m pytest tests/test_gpu_multi.py -q -x 2>&1 | tail -15 > gpurun_out/pytest_gpu_multi_n2.log
 tail -5 gpurun_out/pytest_gpu_multi_n2.log
+fi
 bench() {  # name, env, args
     name=$1; shift; envs=$1; shift
     env $envs python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
