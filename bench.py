@@ -519,8 +519,11 @@ def main():
                     help="multi-GPU halo: direct NVLink peer stores from the fused kernel, or NCCL send/recv")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    # the JSON line is the only thing on stdout: whatever the front ends print or log goes to stderr
-    out = sys.stdout
+    # the JSON line is the only thing on stdout: whatever the front ends, NCCL ("NCCL version ..." comes
+    # from C) or the build tools print goes to stderr -- at the file-descriptor level
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     sys.stdout = sys.stderr
 
     ctx = Context(args)

@@ -663,7 +663,13 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
         }
     }
     cudaError_t e = cudaStreamCreate(&s->stream);
-    if (e == cudaSuccess) e = cudaStreamCreate(&s->comm_stream);
+    {
+        // the communication stream outranks the compute stream: the halo exchange that overlaps the inner
+        // cells must get SM slots as they free up instead of queueing behind the fused kernel's grid
+        int least = 0, greatest = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&s->comm_stream, cudaStreamDefault, greatest);
+    }
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_stop);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_ready, cudaEventDisableTiming);

@@ -13,7 +13,7 @@ bench() {  # name, env, args
 import json, sys
 name = sys.argv[1]
 try:
-    d = json.load(open("gpurun_out/%s.json" % name))
+    d = json.loads([l for l in open("gpurun_out/%s.json" % name) if l.startswith("{")][-1])
     print("%-22s %10.1f MLUPS  %8.4f ms/step  frac %.3f  parity %s  e2e %s" % (
         name, d["value"], d["ms_per_step"], d["frac_of_roofline"],
         d["parity"] and (d["parity"]["ok"], d["parity"]["max_rel_err"]), d["e2e"] and round(d["e2e"]["value"])))
