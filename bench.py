@@ -66,6 +66,7 @@ DEFAULT_WORKLOAD = "d3q19_lid_512"
 ALSO_1GPU = [("d2q9_lid_256", 2000), ("d2q9_karman_4096x1024", 400), ("d2q4x3_shallow_water_4096", 100),
              ("d3q27_channel_512x256x256", 40)]
 ALSO_NGPU = [("d3q27_channel_weak", 30)]
+ALSO_WITH_REFERENCE = {"d2q9_lid_256"}      # BASELINE config 1 is the reference's own CPU-runnable case
 # size of the reference's CPU sample per case: the reference builds dense [unvtot, nx, ny, nz] arrays
 # (domain.py:285-293) and runs on one core, so the big configurations are sampled at reduced size
 REFERENCE_SAMPLE = {
@@ -451,6 +452,14 @@ def measure_also(ctx, workload, steps):
         "scaling": "weak" if workload in WEAK else "strong", "setup_s": round(setup, 2),
     }
     del sim
+    if workload in ALSO_WITH_REFERENCE and ctx.world == 1 and not ctx.args.no_cpu_baseline:
+        # the configuration the reference runs as it is on a CPU: its Cython generator beside the number
+        try:
+            res = reference_cython_run((case_name, case_kw), 20, 3)
+            if res is not None:
+                out["cpu_baseline"] = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        except Exception as exc:
+            out["cpu_baseline"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     return out
 
 
