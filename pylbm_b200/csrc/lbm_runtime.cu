@@ -594,6 +594,8 @@ struct lbm_sim {
     uint64_t up_bytes[2] = {0, 0};
     cudaEvent_t up_event[2] = {nullptr, nullptr};
     int up_next = 0;
+    void* xbuf[4] = {nullptr, nullptr, nullptr, nullptr};   // NCCL halo: packed send / receive planes
+    size_t xbuf_bytes[4] = {0, 0, 0, 0};
     int xchg_inflight = 0;                        // NCCL halo: the exchange for the CURRENT f was issued on
                                                   // comm_stream during the previous step (ev_comm marks its end)
     int overlap = 1;                              // NCCL halo: exchange of step s+1 || inner cells of step s
@@ -723,6 +725,7 @@ extern "C" void lbm_sim_destroy(lbm_sim* s) {
     if (s->wait_err) cudaFreeHost(s->wait_err);
     // (communicators are shared between the time-step objects of a process and live as long as it does)
     free_tasks(s);
+    for (int i = 0; i < 4; ++i) cudaFree(s->xbuf[i]);
     for (int i = 0; i < 2; ++i) {
         if (s->up_buf[i]) cudaFreeHost(s->up_buf[i]);
         if (s->up_event[i]) cudaEventDestroy(s->up_event[i]);
@@ -978,9 +981,47 @@ extern "C" int lbm_sim_set_scalars(lbm_sim* s, const double* scalars, int n) {
 }
 
 // ---- pieces of one step -----------------------------------------------------
+// planes of the selected populations <-> one contiguous buffer [population][plane cells]
+template <typename S>
+__global__ void k_planes(S* __restrict__ f, S* __restrict__ buf, PopSel sel, int side_bit, long long pstride,
+                         long long first, long long count, int to_buf) {
+    // `first` = element position of the first plane inside population 0 (lead + plane * stride)
+    int nsel = 0;
+    unsigned char ks[64];
+    for (int i = 0; i < sel.n; ++i)
+        if (sel.side[i] & side_bit) ks[nsel++] = sel.k[i];
+    const long long total = (long long)nsel * count;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long p = i / count, j = i - p * count;
+        S* a = f + (long long)ks[p] * pstride + first + j;
+        if (to_buf) buf[i] = *a; else *a = buf[i];
+    }
+}
+
+static cudaError_t launch_planes(lbm_sim* s, void* f, void* buf, int side_bit, long long first, long long count,
+                                 int nsel, int to_buf, cudaStream_t st) {
+    const long long total = (long long)nsel * count;
+    if (total <= 0) return cudaSuccess;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    const int a = s->slab_axis;
+    if (s->d.storage == LBM_STORAGE_F64)
+        k_planes<double><<<(unsigned)blocks, 256, 0, st>>>((double*)f, (double*)buf, s->sel[a], side_bit,
+                                                            s->d.grid.pstride, first, count, to_buf);
+    else
+        k_planes<float><<<(unsigned)blocks, 256, 0, st>>>((float*)f, (float*)buf, s->sel[a], side_bit,
+                                                           s->d.grid.pstride, first, count, to_buf);
+    s->launches += 1;
+    return cudaGetLastError();
+}
+
 static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
     // planes [w, 2w) go to the left neighbour's right ghost, planes [n-2w, n-w) to the right
-    // neighbour's left ghost (periodic ring, like the reference's Cartesian communicator).
+    // neighbour's left ghost (periodic ring, like the reference's Cartesian communicator).  Only the
+    // populations that enter the neighbour through that face travel (sign-matched, PopSel), packed into
+    // ONE message per direction: 2 sends + 2 receives per step instead of one pair per population
+    // (20 messages of 2.2 MB for D3Q19 at 512^3 cost 0.54 ms of per-message overhead on 8 GPUs).
     const lbmk_grid& g = s->d.grid;
     const int a = s->slab_axis;
     const int w = s->d.vmax[a];
@@ -991,21 +1032,41 @@ static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
     const int left = (s->rank + s->nranks - 1) % s->nranks, right = (s->rank + 1) % s->nranks;
     const size_t esz = (s->d.storage == LBM_STORAGE_F64) ? 8 : 4;
     const int dtype = (s->d.storage == LBM_STORAGE_F64) ? NCCL_FLOAT64 : NCCL_FLOAT32;
-    char* base = (char*)f;
-    NCCL_TRY(g_nccl.GroupStart());
     const PopSel& sel = s->sel[a];
+    int n_neg = 0, n_pos = 0;          // populations moving in -axis (side bit 2) / +axis (side bit 1)
     for (int i = 0; i < sel.n; ++i) {
-        const long long p = (long long)sel.k[i] * g.pstride + g.lead;
-        // receives first from the right, then from the left: with 2 ranks both neighbours are the
-        // same peer and messages are matched in posting order.  The high ghost layer is only read
-        // for populations moving in -axis (side bit 1), the low one for +axis (side bit 0).
-        if (sel.side[i] & 2) NCCL_TRY(g_nccl.Recv(base + (p + (n - w) * stride) * esz, count, dtype, right, s->comm, st));
-        if (sel.side[i] & 1) NCCL_TRY(g_nccl.Recv(base + p * esz, count, dtype, left, s->comm, st));
-        if (sel.side[i] & 2) NCCL_TRY(g_nccl.Send(base + (p + w * stride) * esz, count, dtype, left, s->comm, st));
-        if (sel.side[i] & 1) NCCL_TRY(g_nccl.Send(base + (p + (n - 2 * w) * stride) * esz, count, dtype, right, s->comm, st));
+        if (sel.side[i] & 2) ++n_neg;
+        if (sel.side[i] & 1) ++n_pos;
     }
+    // buffers: [0] send to the left (neg), [1] send to the right (pos), [2] recv from the right (neg),
+    // [3] recv from the left (pos)
+    const size_t need[4] = {(size_t)n_neg * count * esz, (size_t)n_pos * count * esz,
+                            (size_t)n_neg * count * esz, (size_t)n_pos * count * esz};
+    for (int i = 0; i < 4; ++i) {
+        if (need[i] > s->xbuf_bytes[i]) {
+            if (s->xbuf[i]) cudaFree(s->xbuf[i]);
+            s->xbuf[i] = nullptr;
+            s->xbuf_bytes[i] = 0;
+            CUDA_TRY(cudaMalloc(&s->xbuf[i], need[i]));
+            s->xbuf_bytes[i] = need[i];
+        }
+    }
+    cudaError_t e = launch_planes(s, f, s->xbuf[0], 2, g.lead + (long long)w * stride, count, n_neg, 1, st);
+    if (e == cudaSuccess) e = launch_planes(s, f, s->xbuf[1], 1, g.lead + (n - 2 * w) * stride, count, n_pos, 1, st);
+    if (e != cudaSuccess) return set_error(-(int)e, "halo pack", cudaGetErrorString(e));
+    NCCL_TRY(g_nccl.GroupStart());
+    // receives first from the right, then from the left: with 2 ranks both neighbours are the same peer
+    // and messages are matched in posting order
+    if (n_neg) NCCL_TRY(g_nccl.Recv(s->xbuf[2], (size_t)n_neg * count, dtype, right, s->comm, st));
+    if (n_pos) NCCL_TRY(g_nccl.Recv(s->xbuf[3], (size_t)n_pos * count, dtype, left, s->comm, st));
+    if (n_neg) NCCL_TRY(g_nccl.Send(s->xbuf[0], (size_t)n_neg * count, dtype, left, s->comm, st));
+    if (n_pos) NCCL_TRY(g_nccl.Send(s->xbuf[1], (size_t)n_pos * count, dtype, right, s->comm, st));
     NCCL_TRY(g_nccl.GroupEnd());
     s->launches += 1;
+    // the high ghost layer is only read for populations moving in -axis, the low one for +axis
+    e = launch_planes(s, f, s->xbuf[2], 2, g.lead + (n - w) * stride, count, n_neg, 0, st);
+    if (e == cudaSuccess) e = launch_planes(s, f, s->xbuf[3], 1, g.lead, count, n_pos, 0, st);
+    if (e != cudaSuccess) return set_error(-(int)e, "halo unpack", cudaGetErrorString(e));
     return 0;
 }
 
