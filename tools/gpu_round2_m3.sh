@@ -24,7 +24,6 @@ PY
 }
 bench n${N}_nccl_packed X=1 --steps 100 --halo nccl --no-e2e --no-also
 if [ "$N" = "8" ]; then
-bench n8_nccl_packed_noverlap PYLBM_B200_NO_OVERLAP=1 --steps 100 --halo nccl --no-e2e --no-also --no-parity
 bench n8_peer_20steps X=1 --steps 20 --no-also --no-parity
 bench n8_peer_20steps_nonuma PYLBM_B200_NO_NUMA=1 --steps 20 --no-also --no-parity
 echo "== NUMA probe"
