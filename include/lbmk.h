@@ -42,13 +42,18 @@ typedef struct {
     int hi[3];        /* one past the last index updated by the launch, per axis     */
     int tx;           /* threads of a 128-thread block laid along i2 (power of two)  */
     int w[3];         /* ghost width per axis (interior = [w, n - w))                */
-    int wrap;         /* bit a set: lbmk_one_time_step also stores, for the cells within
+    int wrap;         /* bit a (a = 0..2) set: lbmk_one_time_step also stores, for the cells within
                          w of a face of axis a, their periodic images into the ghost layer
-                         (= the ghost update of the NEXT step, storage.py:333-367)    */
+                         (= the ghost update of the NEXT step, storage.py:333-367);
+                         LBMK_WRAP_PDL set: launch with programmatic stream serialization (the
+                         kernel may be scheduled before the previous kernel of the stream has
+                         finished; it touches memory only after griddepcontrol.wait)        */
     int64_t pitch;    /* elements between consecutive rows                           */
     int64_t lead;     /* position of logical index i2 = 0 inside a row               */
     int64_t pstride;  /* elements between consecutive populations                    */
 } lbmk_grid;
+
+#define LBMK_WRAP_PDL 0x100
 
 /*
  * Neighbour slabs of a multi-GPU run (one process per GPU, x-slabs).  When given, the fused kernel

@@ -40,6 +40,37 @@ static int set_error(int code, const char* what, const char* detail) {
 
 #define ARG_ERROR(msg) set_error(-2001, "argument error", msg)
 
+// ---------------------------------------------------------------------------
+// programmatic dependent launch (sm_90+): the kernels of a time step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization.  Each of them starts with
+//     griddepcontrol.launch_dependents;   the next kernel of the stream may be scheduled as soon as all
+//                                         blocks of this one have started
+//     griddepcontrol.wait;                nothing is read or written before the previous kernel has
+//                                         completed and its memory operations are visible
+// so results are unchanged and the kernel-to-kernel latency of a step (1-2 us per dependent launch,
+// most of the 5 us step of a 256^2 lattice) overlaps with the tail of the previous kernel.  Both
+// instructions are no-ops in a kernel launched without the attribute.
+// ---------------------------------------------------------------------------
+#define LBM_PDL_PROLOGUE()                                         \
+    asm volatile("griddepcontrol.launch_dependents;");             \
+    asm volatile("griddepcontrol.wait;" ::: "memory")
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+static bool g_pdl = true;      // PYLBM_B200_NO_PDL=1 switches it off (lbm_sim_create reads the variable)
+
 extern "C" int lbm_abi_version(void) { return LBM_ABI_VERSION; }
 extern "C" const char* lbm_last_error(void) { return g_err; }
 
@@ -337,6 +368,7 @@ template <typename S, int KIND, int PHASE>
 __global__ void k_bc(S* __restrict__ f, long long ncond, const long long* __restrict__ istore,
                      const long long* __restrict__ iload0, const long long* __restrict__ iload1,
                      const double* __restrict__ rhs, const double* __restrict__ dist, double* __restrict__ scratch) {
+    LBM_PDL_PROLOGUE();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= ncond) return;
     if (PHASE == 2) {
@@ -362,14 +394,15 @@ static cudaError_t launch_bc_kind(S* f, long long n, const long long* is, const 
     if (n <= 0) return cudaSuccess;
     const unsigned blocks = (unsigned)((n + 127) / 128);
     if (!two_phase) {
-        k_bc<S, KIND, 0><<<blocks, 128, 0, st>>>(f, n, is, l0, l1, rhs, dist, scratch);
+        cudaError_t e = launch_k(k_bc<S, KIND, 0>, dim3(blocks), dim3(128), st, g_pdl, f, n, is, l0, l1, rhs, dist, scratch);
         if (nlaunch) ++*nlaunch;
-    } else {
-        k_bc<S, KIND, 1><<<blocks, 128, 0, st>>>(f, n, is, l0, l1, rhs, dist, scratch);
-        k_bc<S, KIND, 2><<<blocks, 128, 0, st>>>(f, n, is, l0, l1, rhs, dist, scratch);
-        if (nlaunch) *nlaunch += 2;
+        return e;
     }
-    return cudaGetLastError();
+    cudaError_t e = launch_k(k_bc<S, KIND, 1>, dim3(blocks), dim3(128), st, g_pdl, f, n, is, l0, l1, rhs, dist, scratch);
+    if (e == cudaSuccess)
+        e = launch_k(k_bc<S, KIND, 2>, dim3(blocks), dim3(128), st, g_pdl, f, n, is, l0, l1, rhs, dist, scratch);
+    if (nlaunch) *nlaunch += 2;
+    return e;
 }
 
 template <typename S>
@@ -409,6 +442,7 @@ struct BcSegments {
 
 template <typename S>
 __global__ void k_bc_multi(S* __restrict__ f, const BcSegments segs) {
+    LBM_PDL_PROLOGUE();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= segs.total) return;
     int m = segs.n - 1;
@@ -518,6 +552,7 @@ extern "C" int lbm_comm_unique_id(void* id128) {
 // Counters only grow and the expected value lives on the device, so the same two kernels can be
 // replayed from a CUDA graph.
 __global__ void k_signal(unsigned long long* to_left, unsigned long long* to_right) {
+    LBM_PDL_PROLOGUE();
     __threadfence_system();
     if (threadIdx.x == 0) atomicAdd_system(to_left, 1ULL);    // I am the RIGHT neighbour of my left rank
     if (threadIdx.x == 1) atomicAdd_system(to_right, 1ULL);   // and the LEFT neighbour of my right rank
@@ -535,6 +570,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
 // ever; the host reports it at the next lbm_sim_sync / lbm_sim_timer_stop / lbm_sim_step.  Once the
 // word is set every later wait returns at once (the results are void from the first miss on).
 __global__ void k_wait(unsigned long long* flags, volatile unsigned int* err, unsigned long long timeout_ns) {
+    LBM_PDL_PROLOGUE();
     // flags[0], flags[1]: arrivals from the left / right neighbour; flags[2], flags[3]: my epochs
     const int i = threadIdx.x;
     if (i < 2) {
@@ -652,6 +688,7 @@ extern "C" lbm_sim* lbm_sim_create(const lbm_sim_desc* desc) {
         const int w = desc->vmax[a];
         if ((desc->periodic_mask & (1 << a)) && w > 0 && desc->grid.n[a] - 2 * w >= 2 * w) s->wrap_mask |= (1 << a);
     }
+    g_pdl = getenv("PYLBM_B200_NO_PDL") == nullptr;
     if (getenv("PYLBM_B200_NO_ZWRAP")) s->wrap_mask &= ~(1 << 2);   // debugging aid: lean copy kernel for z
     if (getenv("PYLBM_B200_NO_WRAP")) s->wrap_mask = 0;             // debugging aid: copy kernels every step
     for (int a = 0; a < 3; ++a) {
@@ -1118,12 +1155,10 @@ static int apply_bcs(lbm_sim* s, void* f, cudaStream_t st) {
         }
         if (segs.total == 0) continue;
         const unsigned blocks = (unsigned)((segs.total + 127) / 128);
-        if (s->d.storage == LBM_STORAGE_F64)
-            k_bc_multi<double><<<blocks, 128, 0, st>>>((double*)f, segs);
-        else
-            k_bc_multi<float><<<blocks, 128, 0, st>>>((float*)f, segs);
+        cudaError_t e = (s->d.storage == LBM_STORAGE_F64)
+                            ? launch_k(k_bc_multi<double>, dim3(blocks), dim3(128), st, g_pdl, (double*)f, segs)
+                            : launch_k(k_bc_multi<float>, dim3(blocks), dim3(128), st, g_pdl, (float*)f, segs);
         s->launches += 1;
-        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return set_error(-(int)e, "boundary kernel", cudaGetErrorString(e));
     }
     return 0;
@@ -1138,7 +1173,7 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
             // fused kernel: just wait for both of them to have finished it (once per array state:
             // lbm_sim_boundary_condition may already have done it)
             if (!s->waited) {
-                k_wait<<<1, 32, 0, st>>>(s->flags, s->wait_err_dev, s->wait_timeout_ns);
+                launch_k(k_wait, dim3(1), dim3(32), st, g_pdl, s->flags, s->wait_err_dev, s->wait_timeout_ns);
                 s->launches += 1;
                 s->waits += 1;
                 s->waited = 1;
@@ -1158,7 +1193,7 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
             if (s->peers_ready && s->waits < s->signals) {
                 // a signal of the previous step is still pending (the ghosts were invalidated from
                 // outside): consume it so that the arrival counters stay in step
-                k_wait<<<1, 32, 0, st>>>(s->flags, s->wait_err_dev, s->wait_timeout_ns);
+                launch_k(k_wait, dim3(1), dim3(32), st, g_pdl, s->flags, s->wait_err_dev, s->wait_timeout_ns);
                 s->launches += 1;
                 s->waits += 1;
             }
@@ -1196,7 +1231,7 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
         cudaEventRecord(ev0, st);
     }
     lbmk_grid g = s->d.grid;
-    g.wrap = s->wrap_mask;
+    g.wrap = s->wrap_mask | (g_pdl ? LBMK_WRAP_PDL : 0);
     lbmk_peers pr;
     if (s->peers_ready) {
         const int which = (fnew == s->buf[0]) ? 0 : 1;   // all ranks swap A/B in lockstep
@@ -1246,7 +1281,7 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
     if (ev1) cudaEventRecord(ev1, st);
     s->launches += 1;
     if (s->peers_ready) {
-        k_signal<<<1, 32, 0, st>>>(s->peer_flags[0] + 1, s->peer_flags[1] + 0);
+        launch_k(k_signal, dim3(1), dim3(32), st, g_pdl, s->peer_flags[0] + 1, s->peer_flags[1] + 0);
         s->launches += 1;
         s->signals += 1;
         s->waited = 0;

@@ -183,8 +183,16 @@ def count_ops(temps, outs):
 _HEADER = r"""// Generated by pylbm_b200.cudagen -- do not edit.  sm_100a.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #define LBMK_ABI_VERSION %(abi)d
+#define LBMK_WRAP_PDL 0x100
+// programmatic dependent launch: the next kernel of the stream may be scheduled once every block of this
+// one has started; nothing is read or written before the previous kernel has completed (no-ops without
+// the launch attribute)
+#define LBMK_PDL_PROLOGUE()                                        \
+    asm volatile("griddepcontrol.launch_dependents;");             \
+    asm volatile("griddepcontrol.wait;" ::: "memory")
 
 extern "C" {
 typedef struct {
@@ -271,6 +279,7 @@ struct lbmk_offs_%(name)s {
 lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g,
     const lbmk_offs_%(name)s offs%(peer_param)s%(scalar_params)s)
 {
+    LBMK_PDL_PROLOGUE();
     constexpr int NQ_ = %(nin)d; (void)NQ_;
     typedef %(tc)s real_c;   // arithmetic type of this kernel
     // 3-D grid: x = chunk of the fastest axis, y = group of `ty` rows of axis 1, z = index of axis 0
@@ -549,24 +558,37 @@ _CALL_PLAIN = """    lbmk_kernel_%(name)s<<<grid, LBMK_BLOCK, 0, (cudaStream_t)s
         (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs%(scalar_args)s);"""
 _CALL_WALLS = """    const lbmk_peers pr_ = peers ? *peers : lbmk_peers{nullptr, nullptr, 0, 0, 0};
     const lbmk_tasks notasks_ = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0};
+    cudaLaunchConfig_t cfg_;
+    memset(&cfg_, 0, sizeof(cfg_));
+    cfg_.gridDim = grid;
+    cfg_.blockDim = dim3(LBMK_BLOCK);
+    cfg_.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr_[1];
+    attr_[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr_[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg_.attrs = attr_;
+    cfg_.numAttrs = (g->wrap & LBMK_WRAP_PDL) ? 1 : 0;
+    lbmk_grid gk_ = *g;
+    gk_.wrap &= 7;
     if (tasks) {
         // the table maps cells to (block, thread) of THIS launch geometry
         if (walls || tasks->tx != g->tx || g->lo[1] != g->w[1] || g->lo[2] != g->w[2] || offs.fold
             || tasks->ngroups_x != (int)grid.x || tasks->ngroups_y != (int)offs.vgy) return -4;
         const size_t smem_ = (size_t)%(nin)d * LBMK_BLOCK * sizeof(real_c_%(name)s) + LBMK_BLOCK * sizeof(unsigned long long);
-        static bool attr_ = false;
-        if (!attr_ && smem_ > 48 * 1024) {
+        static bool attr_set_ = false;
+        if (!attr_set_ && smem_ > 48 * 1024) {
             cudaFuncSetAttribute(lbmk_kernel_%(name)s<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
-            attr_ = true;
+            attr_set_ = true;
         }
-        lbmk_kernel_%(name)s<false, true><<<grid, LBMK_BLOCK, smem_, (cudaStream_t)stream>>>(
-            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, lbmk_walls{}, *tasks%(scalar_args)s);
+        cfg_.dynamicSmemBytes = smem_;
+        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<false, true>,
+            (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, lbmk_walls{}, *tasks%(scalar_args)s);
     } else if (walls)
-        lbmk_kernel_%(name)s<true, false><<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
-            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, *walls, notasks_%(scalar_args)s);
+        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<true, false>,
+            (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, *walls, notasks_%(scalar_args)s);
     else
-        lbmk_kernel_%(name)s<false, false><<<grid, LBMK_BLOCK, 0, (cudaStream_t)stream>>>(
-            (const %(tin)s*)fin, (%(tout)s*)fout, *g, offs, pr_, img, lbmk_walls{}, notasks_%(scalar_args)s);"""
+        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<false, false>,
+            (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, lbmk_walls{}, notasks_%(scalar_args)s);"""
 
 
 def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0, compute="double", cpt=1):

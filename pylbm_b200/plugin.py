@@ -81,7 +81,7 @@ def _split_index(indexed):
         syms = [s for s in idx.free_symbols if s.name in _LOOP]
         if len(syms) != 1:
             raise NotImplementedError("unsupported index %s in %s" % (idx, indexed))
-        shift = sp.simplify(idx - syms[0])
+        shift = sp.expand(idx - syms[0])           # (expand, not simplify: 19-27 populations x Q terms)
         if not shift.is_Integer:
             raise NotImplementedError("non-constant shift in %s" % indexed)
         offset[_LOOP[syms[0].name]] = int(shift)

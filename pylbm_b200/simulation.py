@@ -535,12 +535,12 @@ class CudaEngine:
 
     # ---- time stepping ------------------------------------------------------
     def _push_scalars(self):
-        self._scalars_unresolved = False
         names = self.kernels.scalars("one_time_step")
         if names and names != ["t"]:
-            values = self._scalar_values("one_time_step")
+            values = self._scalar_values("one_time_step")      # KeyError for a symbol without a value
             arr = (ctypes.c_double * len(values))(*values)
             rt.check(rt.lib().lbm_sim_set_scalars(self._handle, arr, len(values)), "lbm_sim_set_scalars")
+        self._scalars_unresolved = False
 
     def _update_time_bc(self):
         for method in self.bc.methods:

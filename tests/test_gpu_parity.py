@@ -387,3 +387,40 @@ def test_time_dependent_boundary_values_on_the_device(monkeypatch):
     ref = run(True, False)
     assert np.array_equal(run(False, False), ref)
     assert np.array_equal(run(False, True), ref)
+
+
+def test_m_halo_setter_keeps_the_other_moments():
+    """`sol.m_halo[k] = v` on the lazily allocated moment array: the other rows keep the moments of the
+    last f2m, like the reference's host array (simulation.py:226-229)."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    sim = pylbm_b200.Simulation(cases.karman_d2q9(nx=64, ny=32, perturb=0))
+    sim.run(4)
+    qx = sim.m_halo[cases.QX].copy()
+    rho = sim.m_halo[cases.RHO].copy()
+    sim.container.release_m()
+    sim._update_m = True
+    sim.m_halo[cases.RHO] = 2.0 * rho
+    assert np.array_equal(sim.m_halo[cases.QX], qx)
+    assert np.array_equal(sim.m_halo[cases.RHO], 2.0 * rho)
+
+
+def test_a_symbol_without_a_value_fails_at_the_first_step():
+    """a kernel scalar that is neither in 'parameters' nor in `extra_parameters` must raise, not run with
+    zero (the reference fails in call_genfunction: algorithm/base.py:662-681)."""
+    import sympy as sp
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    grav = sp.Symbol("gravity_coeff")
+    dico = cases.rayleigh_benard(nx=32, ny=16, time_bc=False)
+    dico["schemes"][0]["source_terms"] = {cases.QY: grav * cases.T}
+    sim = pylbm_b200.Simulation(dico)
+    with pytest.raises(KeyError):
+        sim.one_time_step()
+    with pytest.raises(KeyError):
+        sim.run(2)
+    sim.extra_parameters[grav] = 0.01
+    sim.one_time_step()
+    assert sim.nt == 1
