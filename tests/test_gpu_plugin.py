@@ -5,8 +5,9 @@ importable reference (oracle/_ref, installed by tools/make_ref.sh), after `pylbm
 * against the fixtures of the unmodified reference's Cython generator (tests/golden/ref_*.npz: boundary
   lists `array_equal`, rhs <= 1e-15, conserved moments after 50 steps <= 1e-12 of max|field|) on the 12
   parity workloads, both lowerings;
-* against the reference's demo regression fixtures (tests/golden/demos: Bouzidi, time-dependent boundary
-  values, vectorial schemes, D3Q6/D3Q15, source terms) with the demos' own loop;
+* against ALL the reference's demo regression fixtures (tests/golden/demos: the 26 demo tests, 3 more demos,
+  7 notebook simulations -- Bouzidi, time-dependent boundary values, vectorial schemes, D3Q6/D3Q15, source
+  terms) with the demos' own loop;
 * against the reference's Cython generator run LIVE in the same process on the same dictionary;
 * the kwargs protocol (`sol.algo.call_function`) and the item properties keep the reference's meaning.
 fp64 tolerance 1e-12 (BASELINE.json north_star).
@@ -82,9 +83,10 @@ def test_reference_ir_lowering_against_reference_fixture(cuda, name, kw):
     assert worst <= TOL, worst
 
 
-DEMOS = ["test2D_karman_vortex_street", "test2D_rayleigh_benard", "test2D_shallow_water", "test2D_lid_driven_cavity",
-         "test2D_orszag_Tang_vortex", "test2D_air_conditioning", "test2D_coude", "test3D_poseuille", "test3D_karman",
-         "test3D_lid_cavity", "test1D_euler", "test1D_advection_reaction", "nb04_1"]
+# every dictionary of the reference's demo regression suite and tutorial notebooks (tests/golden/demos)
+from demo_fixtures import demo_names
+
+DEMOS = demo_names()
 
 
 @pytest.mark.parametrize("test", DEMOS)
