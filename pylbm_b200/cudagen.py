@@ -744,7 +744,11 @@ def default_minblocks(nv, compute="double", cpt=1):
         return int(env)
     if cpt > 1:          # the raw loads of the other cells stay live while one cell is computed
         return 6 if compute == "float" else 4
-    return 8 if compute == "float" else 5
+    if compute == "float":
+        return 8
+    # fp64: D3Q27 (27 x 2 registers of populations alone) spills at 5 blocks; measured on the 512x256x256
+    # channel: (128, 4) 2.385 ms, (128, 5) 2.408 ms, (128, 6) 2.447 ms per step
+    return 4 if nv >= 24 else 5
 
 
 def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):

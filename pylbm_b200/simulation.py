@@ -83,6 +83,10 @@ class CudaContainer:
         self.nv = int(scheme.stencil.nv_ptr[-1])
         self.nspace = domain.global_size
         self.vmax = list(domain.stencil.vmax)
+        if sorder is not None and sorted(int(i) for i in sorder) != list(range(self.dim + 1)):
+            raise ValueError("sorder must be a permutation of range(dim + 1), got %r" % (sorder,))
+        # one device layout ([population][x][y][z], padded rows): the reference's `sorder` permutes a
+        # host array (storage.py:60-118); here the argument is validated and has no effect
         self.sorder = [i for i in range(self.dim + 1)]
         shape = domain.shape_halo
         self.F = DeviceArray(self.nv, shape, self.vmax, storage, scheme.consm)
