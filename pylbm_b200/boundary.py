@@ -31,7 +31,7 @@ from .storage import HostArray
 
 __all__ = [
     "Boundary", "BoundaryMethod", "BounceBack", "BouzidiBounceBack", "AntiBounceBack",
-    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule", "merge_groups", "plan_walls", "plan_tasks",
+    "BouzidiAntiBounceBack", "Neumann", "NeumannX", "NeumannY", "NeumannZ", "schedule", "merge_groups", "plan_walls", "plan_tasks", "plan_aa",
 ]
 
 
@@ -206,6 +206,50 @@ def plan_walls(methods, array, velocities, symmetric):
             if ((c2 < w[2]) | (c2 >= n[2] - w[2])).any():
                 return None
     return walls, masks
+
+
+def plan_aa(methods, array, velocities, symmetric):
+    """
+    Boundary lists of the ODD steps of in-place streaming (AA pattern, include/lbm_b200.h:
+    lbm_sim_set_aa).  After an even step the array holds the new population k of cell x in the slot
+    (kbar, x + v_k); every position (k, y) of a list is therefore read / written at (kbar, y + v_k) -- a
+    bijection of the slots, so levels, snapshots and the order of the methods carry over unchanged.
+
+    methods    [{"store", "loads": [positions, ...], ...}] device positions, device order
+    Returns the list of transformed methods (same dictionaries with "store" / "loads" replaced), or None
+    when a transformed position would leave the array (an entry that touches the outermost ghost layer
+    against its own velocity: not produced by the reference's list builders).
+    """
+    dim = array.dim
+    n = array.canonical_n
+    pstride, pitch, lead = array.pstride, array.pitch, array.lead
+    vel = np.zeros((len(velocities), 3), dtype=np.int64)
+    vel[:, 3 - dim:] = np.asarray(velocities, dtype=np.int64)[:, :dim]
+    sym = np.asarray(symmetric, dtype=np.int64)
+    voff = (vel[:, 0] * n[1] + vel[:, 1]) * pitch + vel[:, 2]
+
+    def transform(pos):
+        pos = np.asarray(pos, dtype=np.int64)
+        k = pos // pstride
+        r = pos - k * pstride - lead
+        row = r // pitch
+        c = [row // n[1], row % n[1], r - row * pitch]
+        for a in range(3):
+            t = c[a] + vel[k, a]
+            if ((t < 0) | (t >= n[a])).any():
+                return None
+        return sym[k] * pstride + (pos - k * pstride) + voff[k]
+
+    out = []
+    for m in methods:
+        store = transform(m["store"])
+        loads = [transform(l) for l in m["loads"]]
+        if store is None or any(l is None for l in loads):
+            return None
+        odd = dict(m)
+        odd["store"], odd["loads"] = store, loads
+        out.append(odd)
+    return out
 
 
 def plan_tasks(methods, array, velocities):
