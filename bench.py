@@ -361,12 +361,14 @@ class Context:
             plugin.configure(slab=slab, nccl_id=self.nccl_id, gather=self.gather_fn(), halo=self.args.halo,
                              compute_dtype=compute)
             dico = cases.CASES[case_name](mod=self.pylbm, generator="cuda", **case_kw)
+            if self.args.in_place:
+                dico["cuda_option"] = {"in_place": True}
             return self.pylbm.Simulation(dico, dtype=dtype)
         import pylbm_b200
 
         dico = cases.CASES[case_name](**case_kw)
         return pylbm_b200.Simulation(dico, dtype=dtype, slab=slab, nccl_id=self.nccl_id, gather=self.gather_fn(),
-                                     compute_dtype=compute)
+                                     compute_dtype=compute, in_place=self.args.in_place)
 
 
 def timed_run(ctx, sim, steps, stepwise=False, graph=True):
@@ -520,6 +522,8 @@ def main():
                     help="arithmetic type of the time-step kernel (default float64; float32 needs --dtype float32)")
     ap.add_argument("--api", default="auto", choices=["auto", "pylbm", "b200"],
                     help="front end: the reference's pylbm.Simulation + plugin (oracle/_ref), or pylbm_b200.Simulation")
+    ap.add_argument("--in-place", action="store_true",
+                    help="in-place streaming (AA pattern): ONE population array (single GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the other BASELINE configs")
@@ -543,7 +547,7 @@ def main():
         case_kw = dict(case_kw, nx=case_kw["nx"] * world)
     # identical in both arms (run-dependent facts go to "run")
     config = {"workload": description, "case": case_name, **case_kw, "storage": args.dtype,
-              "arithmetic": args.compute or "float64",
+              "arithmetic": args.compute or "float64", **({"streaming": "in place (one array)"} if args.in_place else {}),
               "l2": "working set (F + Fnew) far larger than the 126 MB L2; no flush needed"}
 
     # ---- reference arm: the reference's CPU implementation alone, rank 0 --------------------------
@@ -620,7 +624,7 @@ def main():
     # every rank: its slab of F from pinned host memory -> HBM, K x sol.one_time_step(), its slab of
     # the conserved moments -> host; wall clock between two barriers, max over ranks
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not args.in_place:
         F = sim.container.F
         nbytes = F.nv * int(np.prod(F.nspace)) * 8
         ptr = ctypes.c_void_p()

@@ -169,6 +169,16 @@ int lbm_sim_set_tasks(lbm_sim* sim, lbmk_launch_tasks_fn launcher, int64_t ntask
                       const int32_t* block_ptr, const uint32_t* code, const int64_t* l0, const int64_t* l1,
                       const double* dist, const int32_t* ibc, const int64_t* entry,
                       int ngroups_y, int ngroups_x, int tx);
+/* In-place streaming (AA pattern): the populations live in ONE array (desc.f == desc.fnew), half the
+ * HBM footprint of the two-array pull scheme, same traffic per step.  `launcher` =
+ * lbmk_one_time_step_aa of a kernel library generated for it.  Steps alternate between the even kernel
+ * (natural -> swapped layout) and the odd kernel (swapped -> natural); after an even step every position
+ * (k, y) of a boundary list is found at (kbar, y + v_k), so each method needs its lists once more in that
+ * form (lbm_sim_set_bc_odd; boundary.plan_aa computes them).  Single GPU, not combined with
+ * lbm_sim_set_walls / lbm_sim_set_tasks.  lbm_sim_aa_phase: 0 natural, 1 swapped, -1 off. */
+int lbm_sim_set_aa(lbm_sim* sim, lbmk_launch_aa_fn launcher);
+int lbm_sim_set_bc_odd(lbm_sim* sim, int ibc, const int64_t* istore, const int64_t* iload0, const int64_t* iload1);
+int lbm_sim_aa_phase(lbm_sim* sim);
 /* Merged launches: the registered methods [group_ptr[g], group_ptr[g+1]) run as ONE kernel launch.
  * The caller must have proved that, inside a group, no entry reads or overwrites a position that an
  * entry of ANOTHER method of the group stores (results are then bit-identical to running the methods

@@ -144,6 +144,16 @@ typedef int (*lbmk_launch_tasks_fn)(const void* fin, void* fout, const lbmk_grid
                                     const lbmk_peers* peers, const lbmk_tasks* tasks, void* stream);
 int lbmk_one_time_step_tasks(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
                              const lbmk_peers* peers, const lbmk_tasks* tasks, void* stream);
+/*
+ * In-place streaming (AA pattern; only in a library generated for it).  ONE array.  phase 0, the even
+ * step: cell x reads (k, x - v_k) like lbmk_one_time_step and stores its new population k into the slot it
+ * read for the opposite population, (kbar, x + v_k) -- plus, for a population that leaves the interior, at
+ * the fully wrapped position (its periodic image).  phase 1, the odd step: cell x reads (kbar, x), which IS
+ * what a pull would bring, and stores (k, x) together with the periodic images of the next even step.
+ * lbmk_f2m_sw / lbmk_f2m_consm_sw read the moments of an array that is in the swapped layout.
+ */
+typedef int (*lbmk_launch_aa_fn)(void* f, const lbmk_grid* g, const double* scalars, int phase, void* stream);
+int lbmk_one_time_step_aa(void* f, const lbmk_grid* g, const double* scalars, int phase, void* stream);
 int lbmk_transport(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_f2m(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 /* conserved moments only: fout has nconsm populations (rows 0..nconsm-1 of M f), same grid */

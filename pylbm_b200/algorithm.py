@@ -269,9 +269,20 @@ class PullAlgorithm:
         stm = self._source_local()
         return self._ir("source_term", "m", self.m, self._zero_offsets(), "m", stm, list(self.m), True)
 
-    def kernels(self):
+    def _swapped(self, ir, name):
+        """the same map reading an in-place (AA) array after an even step: population k of cell x sits in
+        slot (kbar, x + v_k) (include/lbm_b200.h: lbm_sim_set_aa); interior cells only."""
+        sym = [int(k) for k in self.scheme.stencil.get_symmetric()]
+        offsets = [tuple(int(c) for c in v) for v in self.velocities]
+        out = self._ir(name, ir.in_array, ir.in_syms, offsets, ir.out_array, ir.statements, ir.outputs, True)
+        out.in_pops = sym
+        return out
+
+    def kernels(self, aa=False):
         out = [self.transport(), self.f2m(), self.f2m_consm(), self.m2f(), self.relaxation(), self.equilibrium(),
                self.one_time_step()]
         if self.source_eq:
             out.append(self.source_term())
+        if aa:
+            out += [self._swapped(self.f2m(), "f2m_sw"), self._swapped(self.f2m_consm(), "f2m_consm_sw")]
         return out

@@ -600,6 +600,8 @@ struct BcMethod {
     int stale_only = 0;      // skipped when the ghost layers come from the previous fused launch
     long long ncond = 0;
     long long *istore = nullptr, *iload0 = nullptr, *iload1 = nullptr;
+    // the same positions seen through an in-place array after an even step: (k, y) -> (kbar, y + v_k)
+    long long *istore_odd = nullptr, *iload0_odd = nullptr, *iload1_odd = nullptr;
     double *rhs = nullptr, *dist = nullptr;
     std::vector<long long> level_ptr;
     std::vector<int> two_phase;
@@ -614,6 +616,8 @@ struct lbm_sim {
     std::vector<int> bc_groups;                   // first method of each merged launch (+ end); empty: none
     lbmk_launch_walls_fn walls_fn = nullptr;      // fused kernel applies the walls of the fastest axis
     lbmk_walls walls;
+    lbmk_launch_aa_fn aa_fn = nullptr;            // in-place streaming: ONE array, even / odd steps
+    int aa_swapped = 0;                           // the array is in the swapped layout (after an even step)
     lbmk_launch_tasks_fn tasks_fn = nullptr;      // fused kernel evaluates the boundary entries itself
     lbmk_tasks tasks;                             // device arrays owned by this object
     double* scratch = nullptr;
@@ -736,6 +740,7 @@ static int check_peers(lbm_sim* s) {
 
 static void free_bc(BcMethod& b) {
     cudaFree(b.istore); cudaFree(b.iload0); cudaFree(b.iload1); cudaFree(b.rhs); cudaFree(b.dist);
+    cudaFree(b.istore_odd); cudaFree(b.iload0_odd); cudaFree(b.iload1_odd);
 }
 
 static void free_tasks(lbm_sim* s) {
@@ -862,6 +867,7 @@ extern "C" int lbm_sim_set_walls(lbm_sim* s, lbmk_launch_walls_fn launcher, cons
     if (!s) return ARG_ERROR("null sim");
     if (walls && !launcher) return ARG_ERROR("lbm_sim_set_walls: launcher missing");
     if (walls && s->tasks_fn) return ARG_ERROR("lbm_sim_set_walls: not combined with lbm_sim_set_tasks");
+    if (walls && s->aa_fn) return ARG_ERROR("lbm_sim_set_walls: not combined with in-place streaming");
     if (walls && !(s->wrap_mask & (1 << 2)))
         // the z periodic copy would run on fresh ghosts and overwrite the wall values the kernel stored
         return ARG_ERROR("lbm_sim_set_walls: the fused kernel does not maintain the ghosts of the fastest axis "
@@ -917,6 +923,44 @@ extern "C" int lbm_sim_set_tasks(lbm_sim* s, lbmk_launch_tasks_fn launcher, int6
     }
     return 0;
 }
+
+extern "C" int lbm_sim_set_bc_odd(lbm_sim* s, int ibc, const int64_t* istore, const int64_t* iload0,
+                                  const int64_t* iload1) {
+    if (!s || ibc < 0 || ibc >= (int)s->bcs.size()) return ARG_ERROR("lbm_sim_set_bc_odd: no such method");
+    BcMethod& b = s->bcs[ibc];
+    if (b.ncond > 0 && (!istore || !iload0 || (b.iload1 && !iload1))) return ARG_ERROR("lbm_sim_set_bc_odd: null lists");
+    cudaFree(b.istore_odd); cudaFree(b.iload0_odd); cudaFree(b.iload1_odd);
+    b.istore_odd = b.iload0_odd = b.iload1_odd = nullptr;
+    cudaError_t e = upload(&b.istore_odd, (const long long*)istore, b.ncond);
+    if (e == cudaSuccess) e = upload(&b.iload0_odd, (const long long*)iload0, b.ncond);
+    if (e == cudaSuccess) e = upload(&b.iload1_odd, (const long long*)iload1, b.iload1 ? b.ncond : 0);
+    if (e != cudaSuccess) return set_error(-(int)e, "lbm_sim_set_bc_odd", cudaGetErrorString(e));
+    drop_graph(s);
+    return 0;
+}
+
+extern "C" int lbm_sim_set_aa(lbm_sim* s, lbmk_launch_aa_fn launcher) {
+    if (!s) return ARG_ERROR("null sim");
+    cudaStreamSynchronize(s->stream);
+    drop_graph(s);
+    if (!launcher) {
+        if (s->aa_swapped) return ARG_ERROR("lbm_sim_set_aa: the array is in the swapped layout (odd number of steps)");
+        s->aa_fn = nullptr;
+        return 0;
+    }
+    if (s->f != s->fnew) return ARG_ERROR("lbm_sim_set_aa: in-place streaming runs on ONE array (desc.f == desc.fnew)");
+    if (s->nranks > 1) return ARG_ERROR("lbm_sim_set_aa: single GPU only");
+    if (s->walls_fn || s->tasks_fn) return ARG_ERROR("lbm_sim_set_aa: not combined with lbm_sim_set_walls / lbm_sim_set_tasks");
+    if (s->wrap_mask != s->d.periodic_mask)
+        return ARG_ERROR("lbm_sim_set_aa: the fused kernel must maintain the images of every ghost axis "
+                         "(an axis is shorter than four ghost widths, or PYLBM_B200_NO_WRAP is set)");
+    s->aa_fn = launcher;
+    s->aa_swapped = 0;
+    s->ghost_fresh = 0;
+    return 0;
+}
+
+extern "C" int lbm_sim_aa_phase(lbm_sim* s) { return !s || !s->aa_fn ? -1 : s->aa_swapped; }
 
 extern "C" int lbm_sim_bc_groups(lbm_sim* s, int ngroups, const int* group_ptr) {
     if (!s) return ARG_ERROR("null sim");
@@ -1109,16 +1153,21 @@ static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
 
 static int apply_bc_method(lbm_sim* s, BcMethod& b, void* f, cudaStream_t st) {
     if (b.stale_only && s->ghost_fresh) return 0;   // the previous fused launch stored these values
+    const bool odd = s->aa_fn && s->aa_swapped;
+    if (odd && b.ncond > 0 && !b.istore_odd) return ARG_ERROR("in-place streaming: odd-step lists missing (lbm_sim_set_bc_odd)");
+    const long long* is_ = odd ? b.istore_odd : b.istore;
+    const long long* l0_ = odd ? b.iload0_odd : b.iload0;
+    const long long* l1_ = odd ? b.iload1_odd : b.iload1;
     for (size_t l = 0; l + 1 < b.level_ptr.size(); ++l) {
         const long long o = b.level_ptr[l], n = b.level_ptr[l + 1] - o;
         if (n <= 0) continue;
         cudaError_t e =
             (s->d.storage == LBM_STORAGE_F64)
-                ? launch_bc<double>(b.kind, (double*)f, n, b.istore + o, b.iload0 + o,
-                                    b.iload1 ? b.iload1 + o : nullptr, b.rhs ? b.rhs + o : nullptr,
+                ? launch_bc<double>(b.kind, (double*)f, n, is_ + o, l0_ + o,
+                                    l1_ ? l1_ + o : nullptr, b.rhs ? b.rhs + o : nullptr,
                                     b.dist ? b.dist + o : nullptr, s->scratch, b.two_phase[l], st, &s->launches)
-                : launch_bc<float>(b.kind, (float*)f, n, b.istore + o, b.iload0 + o,
-                                   b.iload1 ? b.iload1 + o : nullptr, b.rhs ? b.rhs + o : nullptr,
+                : launch_bc<float>(b.kind, (float*)f, n, is_ + o, l0_ + o,
+                                   l1_ ? l1_ + o : nullptr, b.rhs ? b.rhs + o : nullptr,
                                    b.dist ? b.dist + o : nullptr, s->scratch, b.two_phase[l], st, &s->launches);
         if (e != cudaSuccess) return set_error(-(int)e, "boundary kernel", cudaGetErrorString(e));
     }
@@ -1149,7 +1198,11 @@ static int apply_bcs(lbm_sim* s, void* f, cudaStream_t st) {
             BcSegment& sg = segs.seg[segs.n++];
             sg.begin = segs.total;
             sg.kind = b.kind;
-            sg.istore = b.istore; sg.iload0 = b.iload0; sg.iload1 = b.iload1;
+            const bool odd = s->aa_fn && s->aa_swapped;
+            if (odd && !b.istore_odd) return ARG_ERROR("in-place streaming: odd-step lists missing (lbm_sim_set_bc_odd)");
+            sg.istore = odd ? b.istore_odd : b.istore;
+            sg.iload0 = odd ? b.iload0_odd : b.iload0;
+            sg.iload1 = odd ? b.iload1_odd : b.iload1;
             sg.rhs = b.rhs; sg.dist = b.dist;
             segs.total += b.ncond;
         }
@@ -1207,6 +1260,45 @@ static int ghost_update(lbm_sim* s, void* f, cudaStream_t st) {
 }
 
 static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) {
+    if (s->aa_fn) {
+        // in-place streaming (AA pattern).  Even step: ghost update, boundary methods, gather + scatter
+        // back (the array is swapped afterwards).  Odd step: boundary methods on the transformed lists
+        // -- no ghost update, the even step stored the wrapped images itself -- then the local kernel,
+        // which leaves the natural layout and the periodic images of the next even step.
+        int rc = 0;
+        if (!s->aa_swapped) {
+            rc = ghost_update(s, f, st);
+            if (rc) return rc;
+        }
+        rc = apply_bcs(s, f, st);
+        if (rc) return rc;
+        double scal[32];
+        for (int i = 0; i < s->d.nscalars; ++i) scal[i] = s->d.scalars[i];
+        if (s->d.t_index >= 0 && s->d.t_index < s->d.nscalars) scal[s->d.t_index] = t;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (s->profile) {
+            if (s->prof_used + 2 > s->prof_events.size()) {
+                cudaEvent_t a, b;
+                if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess)
+                    return set_error(-2002, "profile", "cannot create events");
+                s->prof_events.push_back(a);
+                s->prof_events.push_back(b);
+            }
+            ev0 = s->prof_events[s->prof_used];
+            ev1 = s->prof_events[s->prof_used + 1];
+            s->prof_used += 2;
+            cudaEventRecord(ev0, st);
+        }
+        lbmk_grid g = s->d.grid;
+        g.wrap = s->wrap_mask | (g_pdl ? LBMK_WRAP_PDL : 0);
+        rc = s->aa_fn(f, &g, scal, s->aa_swapped, (void*)st);
+        if (rc) return set_error(rc, "in-place kernel launch", cudaGetErrorString((cudaError_t)(-rc)));
+        if (ev1) cudaEventRecord(ev1, st);
+        s->launches += 1;
+        s->aa_swapped ^= 1;
+        s->ghost_fresh = s->aa_swapped ? 0 : 1;     // the odd kernel wrote the images of the next even step
+        return 0;
+    }
     int rc = ghost_update(s, f, st);
     if (rc) return rc;
     if (!s->tasks_fn) {          // with a task table the fused kernel evaluates the entries itself
@@ -1322,7 +1414,7 @@ extern "C" int lbm_sim_step(lbm_sim* s, int nsteps) {
     while (done < nsteps) {
         // pairs of steps (f -> fnew -> f) are replayed from a CUDA graph once the ghost layers are
         // maintained by the fused kernel itself (no copy kernels / NCCL calls inside the capture)
-        if (graph_ok && s->ghost_fresh && !s->waited && nsteps - done >= 2) {
+        if (graph_ok && s->ghost_fresh && !s->waited && nsteps - done >= 2 && !(s->aa_fn && s->aa_swapped)) {
             if (!s->graph || s->graph_f != s->f) {
                 int rc = build_graph(s);
                 if (rc) return rc;
@@ -1348,8 +1440,10 @@ extern "C" int lbm_sim_step(lbm_sim* s, int nsteps) {
 
 extern "C" int lbm_sim_boundary_condition(lbm_sim* s) {
     if (!s) return ARG_ERROR("null sim");
-    int rc = ghost_update(s, s->f, s->stream);
-    if (rc) return rc;
+    if (!(s->aa_fn && s->aa_swapped)) {
+        int rc = ghost_update(s, s->f, s->stream);
+        if (rc) return rc;
+    }
     return apply_bcs(s, s->f, s->stream);
 }
 
@@ -1490,6 +1584,7 @@ extern "C" int lbm_sim_ipc_open(lbm_sim* s, const void* left_blob, const void* r
 
 extern "C" int lbm_sim_comm_init(lbm_sim* s, int rank, int nranks, const void* id128) {
     if (!s || nranks < 1 || rank < 0 || rank >= nranks) return ARG_ERROR("lbm_sim_comm_init");
+    if (s->aa_fn && nranks > 1) return ARG_ERROR("lbm_sim_comm_init: in-place streaming is single GPU only");
     s->rank = rank;
     s->nranks = nranks;
     if (nranks == 1) return 0;

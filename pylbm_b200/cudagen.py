@@ -241,6 +241,15 @@ typedef struct {       // boundary entries evaluated by the pulling thread (see 
 #define SLAB %(slab)d
 
 typedef %(storage)s real_f;   // storage type of the populations in HBM
+// a library generated for in-place streaming launches the fused kernel with fin == fout: no __restrict__,
+// no non-coherent loads there
+#if %(aa)d
+#define LBMK_RESTRICT
+#define LBMK_LDG(p) (*(p))
+#else
+#define LBMK_RESTRICT __restrict__
+#define LBMK_LDG(p) __ldg(p)
+#endif
 // fp32 -> fp64 on the integer pipe (exact for normal numbers: rebias the exponent, widen the mantissa);
 // zero, subnormals, inf and nan take the conversion instruction.  Experiment: PYLBM_B200_F2D=int.
 __device__ __forceinline__ double lbmk_f2d(float x) {
@@ -276,11 +285,11 @@ struct lbmk_offs_%(name)s {
 };
 
 %(template)s__global__ void __launch_bounds__(LBMK_BLOCK, %(minblocks)d)
-lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fout, const lbmk_grid g,
+lbmk_kernel_%(name)s(const %(tin)s* %(restrict)s fin, %(tout)s* %(restrict)s fout, const lbmk_grid g,
     const lbmk_offs_%(name)s offs%(peer_param)s%(scalar_params)s)
 {
     LBMK_PDL_PROLOGUE();
-    constexpr int NQ_ = %(nin)d; (void)NQ_;
+%(mode_decl)s    constexpr int NQ_ = %(nin)d; (void)NQ_;
     typedef %(tc)s real_c;   // arithmetic type of this kernel
     // 3-D grid: x = chunk of the fastest axis, y = group of `ty` rows of axis 1, z = index of axis 0
     // (no integer division in the prologue; tx is a power of two)
@@ -325,8 +334,10 @@ lbmk_kernel_%(name)s(const %(tin)s* __restrict__ fin, %(tout)s* __restrict__ fou
         grid.z = (unsigned)gz;
     }
     const long long plane = (long long)g->n[1] * g->pitch;
+    static const int inpop_[%(nin)d] = {%(inpop_table)s};   // population read as input k (identity, or the
+                                                          // opposite population for a swapped in-place array)
     for (int k = 0; k < %(nin)d; ++k)
-        offs.in[k] = (k * g->pstride + noff[k][0] * plane + noff[k][1] * g->pitch + noff[k][2]) * (long long)sizeof(%(tin)s);
+        offs.in[k] = (inpop_[k] * g->pstride + noff[k][0] * plane + noff[k][1] * g->pitch + noff[k][2]) * (long long)sizeof(%(tin)s);
     for (int k = 0; k < %(nout)d; ++k)
         offs.out[k] = k * g->pstride * (long long)sizeof(%(tout)s);
     for (int k = 0; k < %(nout)d; ++k) offs.wall[k] = 0;
@@ -354,6 +365,7 @@ _IMAGES_PROLOGUE = r"""    // ---- periodic / neighbour images of this cell (see
     const long long d2 = WALLZ ? 0LL : (i2 < img.below[2] ? img.dlow[2] : (i2 >= img.above[2] ? img.dhigh[2] : 0LL));
     const bool wlo = WALLZ && i2 == walls.lo_plane, whi = WALLZ && i2 == walls.hi_plane;
     (void)wlo; (void)whi;
+%(aa_shifts)s
     // array receiving the images that cross the SLAB axis (a neighbour's array with the peer halo)
     %(tout)s* qbase = fout;
     long long qps = g.pstride;
@@ -383,11 +395,15 @@ _IMAGES_LAUNCH = r"""
             img.dlow[a] = on ? (long long)(peer_ ? pp->nin_lo : nin) * stride_[a] : 0;
             img.dhigh[a] = on ? -(long long)nin * stride_[a] : 0;
         }
-        // bounced population sym(k) at the neighbour c + v_k = c - noff[k] (only used with walls)
+        // bounced population sym(k) at the neighbour c + v_k = c - noff[k] (walls; in-place even step)
         static const int sym_[%(nout)d] = {%(sym_table)s};
         for (int k = 0; k < %(nout)d; ++k)
             offs.wall[k] = (sym_[k] * g->pstride - (noff[k][0] * stride_[0] + noff[k][1] * stride_[1] + noff[k][2]))
                            * (long long)sizeof(%(tout)s);
+        // in-place streaming (AA pattern): the even step stores population k into the slot it read for the
+        // opposite population, (sym k, c + v_k); the odd step reads population k from (sym k, c)
+        if (aa_phase == 1) for (int k = 0; k < %(nout)d; ++k) offs.out[k] = offs.wall[k];
+        if (aa_phase == 2) for (int k = 0; k < %(nout)d; ++k) offs.in[k] = sym_[k] * g->pstride * (long long)sizeof(%(tout)s);
     }
 """
 
@@ -479,8 +495,14 @@ def _inline_image(v, k, slab, tout):
     instantiation the same lanes store the bounced value into the wall's ghost cell instead
     (bounce_back / anti_bounce_back of the NEXT step, reference boundary.py:462-464, 678-680, with the
     arithmetic of the list kernel k_bc: explicit round-to-nearest add, no contraction)."""
+    aa_terms = ["aa%s%d_%d" % ("P" if v[a] > 0 else "M", a, abs(v[a])) for a in range(3) if v[a] != 0]
+    aa = ""
+    if aa_terms:
+        # in-place even step: a population that leaves the interior is also stored at the fully wrapped
+        # position (its periodic image); the unwrapped store above is what the boundary kernels read
+        aa = " if (AAEVEN) { const long long wr_ = %s; if (wr_) __stcg(p_ + wr_, o_); }" % " + ".join(aa_terms)
     if v[2] == 0:
-        return ""
+        return aa
     cond = "p2" if v[2] > 0 else "m2"
     if slab == 2:
         image = " if (%s) qbase[%dLL * qps + cell + d2] = o_;" % (cond, k)
@@ -489,7 +511,7 @@ def _inline_image(v, k, slab, tout):
     wall, neg = ("wlo", "walls.neg_lo") if v[2] < 0 else ("whi", "walls.neg_hi")
     bounce = (" if (%s) __stcg((%s*)(pout + offs.wall[%d]), (%s)__dadd_rn(%s ? -(double)o_ : (double)o_, walls.rhs[%d]));"
               % (wall, tout, k, tout, neg, k))
-    return " if (!WALLZ) {%s } else {%s }" % (image, bounce)
+    return aa + " if (!AAEVEN) { if (!WALLZ) {%s } else {%s } }" % (image, bounce)
 
 
 def _images_code(velocities, tout, slab):
@@ -497,7 +519,7 @@ def _images_code(velocities, tout, slab):
     or 1 (cells of whole boundary rows / planes: full warps, rare)."""
     import itertools
 
-    lines = ["    if (d0 | d1) {"]
+    lines = ["    if (!AAEVEN && (d0 | d1)) {"]
     dname = ["d0", "d1", "d2"]
     moving = [k for k, v in enumerate(velocities) if v[0] != 0 or v[1] != 0]
     # re-read this thread's own stores, all loads issued back to back (one memory latency)
@@ -530,7 +552,14 @@ def _canonical(offset):
 _LAUNCH_HEAD = 'extern "C" int lbmk_%(name)s(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream)'
 _LAUNCH_HEAD_WALLS = ('static int lbmk_launch_%(name)s_(const void* fin, void* fout, const lbmk_grid* g, '
                       'const double* scalars, const lbmk_peers* peers, const lbmk_walls* walls, '
-                      'const lbmk_tasks* tasks, void* stream)')
+                      'const lbmk_tasks* tasks, void* stream, int aa_phase = 0)')
+_LAUNCH_TAIL_AA = """
+// in-place streaming: ONE array; phase 0 = even step (gather, scatter back), phase 1 = odd step (local)
+extern "C" int lbmk_%(name)s_aa(void* f, const lbmk_grid* g, const double* scalars, int phase, void* stream)
+{
+    return lbmk_launch_%(name)s_(f, f, g, scalars, nullptr, nullptr, nullptr, stream, phase ? 2 : 1);
+}
+"""
 _LAUNCH_TAIL_WALLS = """
 extern "C" int lbmk_%(name)s_tasks(const void* fin, void* fout, const lbmk_grid* g, const double* scalars,
                                    const lbmk_peers* peers, const lbmk_tasks* tasks, void* stream)
@@ -577,21 +606,25 @@ _CALL_WALLS = """    const lbmk_peers pr_ = peers ? *peers : lbmk_peers{nullptr,
         const size_t smem_ = (size_t)%(nin)d * LBMK_BLOCK * sizeof(real_c_%(name)s) + LBMK_BLOCK * sizeof(unsigned long long);
         static bool attr_set_ = false;
         if (!attr_set_ && smem_ > 48 * 1024) {
-            cudaFuncSetAttribute(lbmk_kernel_%(name)s<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
+            cudaFuncSetAttribute(lbmk_kernel_%(name)s<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_);
             attr_set_ = true;
         }
         cfg_.dynamicSmemBytes = smem_;
-        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<false, true>,
+        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<0, true>,
             (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, lbmk_walls{}, *tasks%(scalar_args)s);
-    } else if (walls)
-        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<true, false>,
+    }%(aa_call)s else if (walls)
+        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<1, false>,
             (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, *walls, notasks_%(scalar_args)s);
     else
-        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<false, false>,
+        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<0, false>,
+            (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, lbmk_walls{}, notasks_%(scalar_args)s);"""
+_CALL_AA = """ else if (aa_phase == 1)
+        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<2, false>,
             (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, lbmk_walls{}, notasks_%(scalar_args)s);"""
 
 
-def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0, compute="double", cpt=1):
+def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, slab=0, compute="double", cpt=1,
+                  aa=False):
     """CUDA source of one per-cell kernel + its C-ABI launcher.  `compute` is the arithmetic type of
     the kernel body (double, or float for the all-fp32 mode of the fused kernel); `cpt` the number of
     cells a thread of the fused kernel computes."""
@@ -623,7 +656,7 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
             parts.append("        unsigned long long pin = (unsigned long long)(fin + cell%d_);" % c)
             parts.append('        asm volatile("" : "+l"(pin));   // keep `pointer + constant-bank offset` as the address form')
             for k in range(nq):
-                parts.append("        r%d_%d = __ldg((const %s*)(pin + offs.in[%d]));" % (c, k, tin, k))
+                parts.append("        r%d_%d = LBMK_LDG((const %s*)(pin + offs.in[%d]));" % (c, k, tin, k))
             parts.append("    }")
         images_tail = _images_code(vels, tout, slab)
         for c in range(cpt):
@@ -639,7 +672,15 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
             for k, sym in enumerate(ir.in_syms):
                 parts.append("        if (tmask_ & (1ull << %d)) %s = sm_val_[%d * LBMK_BLOCK + tid];" % (k, sym, k))
             parts.append("    }")
-            parts.append(_IMAGES_PROLOGUE % dict(tout=tout))
+            shifts = []
+            for a in range(3):
+                for mag in sorted({abs(v[a]) for v in vels if v[a] != 0}):
+                    shifts.append("    const long long aaP%d_%d = (AAEVEN && i%d + %d >= g.n[%d] - g.w[%d]) ? img.dhigh[%d] : 0LL;"
+                                  % (a, mag, a, mag, a, a, a))
+                    shifts.append("    const long long aaM%d_%d = (AAEVEN && i%d - %d < g.w[%d]) ? img.dlow[%d] : 0LL;"
+                                  % (a, mag, a, mag, a, a))
+                    shifts.append("    (void)aaP%d_%d; (void)aaM%d_%d;" % (a, mag, a, mag))
+            parts.append(_IMAGES_PROLOGUE % dict(tout=tout, aa_shifts="\n".join(shifts)))
             parts.extend(body)
             parts.extend(stores)
             parts.append(images_tail)
@@ -675,14 +716,19 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         scalar_args=scal_args,
         offset_table=table,
         thread_body=thread_body,
-        template="template <bool WALLZ, bool TASKS>\n" if images else "",
+        template="template <int MODE, bool TASKS>\n" if images else "",
+        mode_decl=("    constexpr bool WALLZ = (MODE == 1), AAEVEN = (MODE == 2); (void)WALLZ; (void)AAEVEN;\n"
+                   if images else ""),
+        restrict="LBMK_RESTRICT" if images else "__restrict__",
+        inpop_table=", ".join(str(int(k)) for k in (getattr(ir, "in_pops", None) or range(nq))),
         peer_param=(", const lbmk_peers pr, const lbmk_images img, const lbmk_walls walls, const lbmk_tasks tasks"
                     if images else ""),
         images_launch=(_IMAGES_LAUNCH % dict(nout=len(outs), tout=tout, sym_table=sym_table)) if images else "",
-        kernel_call=(_CALL_WALLS if images else _CALL_PLAIN) % dict(name=ir.name, tin=tin, tout=tout,
-                                                                    scalar_args=scal_args, nin=nq),
+        kernel_call=(_CALL_WALLS if images else _CALL_PLAIN) % dict(
+            name=ir.name, tin=tin, tout=tout, scalar_args=scal_args, nin=nq,
+            aa_call=(_CALL_AA % dict(name=ir.name, tin=tin, tout=tout, scalar_args=scal_args)) if (images and aa) else ""),
         launch_head=(_LAUNCH_HEAD_WALLS if images else _LAUNCH_HEAD) % dict(name=ir.name),
-        launch_tail=(_LAUNCH_TAIL_WALLS % dict(name=ir.name)) if images else "",
+        launch_tail=((_LAUNCH_TAIL_WALLS + (_LAUNCH_TAIL_AA if aa else "")) % dict(name=ir.name)) if images else "",
     )
     # user symbols may not be valid C identifiers (e.g. `lambda`)
     for s_ in ir.scalars:
@@ -751,7 +797,7 @@ def default_minblocks(nv, compute="double", cpt=1):
     return 4 if nv >= 24 else 5
 
 
-def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):
+def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double", aa=False):
     """
     Cache key of a kernel library: hash of the IR (deterministic across processes, unlike the text
     produced by sympy.cse whose temporaries depend on set ordering), of the generator options and
@@ -764,10 +810,11 @@ def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):
 
     cpt = default_cpt(storage)
     h.update(repr((ABI_VERSION, dim, nv, storage, cse, default_minblocks(nv, compute, cpt), compute, cpt,
-                   os.environ.get("PYLBM_B200_F2D", ""))).encode())
+                   os.environ.get("PYLBM_B200_F2D", ""), bool(aa))).encode())
     for ir in kernels:
         h.update(repr((ir.name, ir.in_array, ir.out_array, bool(ir.inner), list(ir.scalars),
-                       [str(s) for s in ir.in_syms], [tuple(o) for o in ir.in_offsets])).encode())
+                       [str(s) for s in ir.in_syms], [tuple(o) for o in ir.in_offsets],
+                       list(getattr(ir, "in_pops", None) or []))).encode())
         for lhs, rhs in ir.statements:
             h.update((str(lhs) + "=" + sp.srepr(sp.sympify(rhs))).encode())
         for out in ir.outputs:
@@ -775,7 +822,7 @@ def kernel_tag(kernels, dim, nv, storage="double", cse=True, compute="double"):
     return h.hexdigest()[:20]
 
 
-def generate_source(kernels, dim, nv, storage="double", cse=True, compute="double"):
+def generate_source(kernels, dim, nv, storage="double", cse=True, compute="double", aa=False):
     """
     Full translation unit for a list of KernelIR.  Returns (source, info dict).
     `storage` is the type of the populations in HBM, `compute` the arithmetic type of the
@@ -786,7 +833,7 @@ def generate_source(kernels, dim, nv, storage="double", cse=True, compute="doubl
         raise ValueError("float arithmetic needs float storage of the populations")
     import json
 
-    parts = [_HEADER % dict(abi=ABI_VERSION, storage=storage, slab=3 - dim)]
+    parts = [_HEADER % dict(abi=ABI_VERSION, storage=storage, slab=3 - dim, aa=1 if aa else 0)]
     info = {"abi": ABI_VERSION, "dim": dim, "nv": nv, "storage": storage, "compute": compute, "routines": {}}
     cpt = default_cpt(storage)
     for ir in kernels:
@@ -794,7 +841,7 @@ def generate_source(kernels, dim, nv, storage="double", cse=True, compute="doubl
         src, ops = kernel_source(ir, storage=storage, cse=cse, images=fused,
                                  minblocks=default_minblocks(nv, compute, cpt) if fused else 1, slab=3 - dim,
                                  compute=compute if ir.name in ("one_time_step", "transport") else "double",
-                                 cpt=cpt)
+                                 cpt=cpt, aa=aa)
         parts.append(src)
         info["routines"][ir.name] = {
             "scalars": list(ir.scalars),
@@ -807,5 +854,6 @@ def generate_source(kernels, dim, nv, storage="double", cse=True, compute="doubl
     literal = '"' + text.replace("\\", "\\\\").replace('"', '\\"') + '"'
     parts.append(_DESCRIBE % dict(json=literal))
     source = "\n".join(parts)
-    info["hash"] = kernel_tag(kernels, dim, nv, storage, cse, compute)
+    info["hash"] = kernel_tag(kernels, dim, nv, storage, cse, compute, aa=aa)
+    info["aa"] = bool(aa)
     return source, info

@@ -246,7 +246,8 @@ class CudaModule:
             from .simulation import build_kernel_library
 
             _, path, source = build_kernel_library(self._context["scheme"], self._context.get("settings"), storage,
-                                                   need_source=need_source, compute=compute)
+                                                   need_source=need_source, compute=compute,
+                                                   aa=bool(self._context.get("aa")))
             self.source = source or self.source
             return rt.KernelLibrary(path)
         kernels = self._ir_kernels()
@@ -371,7 +372,8 @@ def configure(**kwargs):
       compute_dtype='float32'                               fp32 arithmetic (with dtype='float32')
       lowering='scheme' | 'ir'                              see the module docstring
     The last two can also be given per simulation as `dico['cuda_option'] = {'compute_dtype': ..,
-    'lowering': ..}` (the only key this backend adds to the reference's dictionary).
+    'lowering': .., 'in_place': True}` (the only key this backend adds to the reference's dictionary;
+    `in_place` = in-place streaming, ONE population array).
     """
     for key, value in kwargs.items():
         if key not in _config:
@@ -524,7 +526,7 @@ def register():
             option = dico.get("cuda_option") or {}
             storage, compute = self._storage_names(dtype, option.get("compute_dtype", _config["compute_dtype"]))
             slab, nccl_id, gather = _process_group()
-            self._engine_defaults(storage, compute, slab, nccl_id, gather)
+            self._engine_defaults(storage, compute, slab, nccl_id, gather, bool(option.get("in_place", False)))
             self._lowering = option.get("lowering", _config["lowering"])
             topology = None
             if self.nranks > 1:
@@ -538,7 +540,7 @@ def register():
 
         # container table (simulation.py:165-171)
         def _get_container(self, sorder):
-            return CudaContainer(self.domain, self.scheme, sorder, self.storage)
+            return CudaContainer(self.domain, self.scheme, sorder, self.storage, self.in_place)
 
         # algorithm (simulation.py:179-190): unchanged, but the generator learns what it compiles for
         def _get_algorithm(self, dico, sorder):
@@ -549,7 +551,9 @@ def register():
                 raise ValueError("cuda_option['lowering'] must be 'scheme' or 'ir', got %r" % (lowering,))
             if lowering == "scheme" and not stock:
                 raise ValueError("cuda_option['lowering']='scheme' only knows the stock PullAlgorithm")
-            context = {"storage": self.storage, "compute": self.compute, "lowering": lowering,
+            if self.in_place and lowering != "scheme":
+                raise NotImplementedError("in-place streaming is generated by the scheme lowering only")
+            context = {"storage": self.storage, "compute": self.compute, "lowering": lowering, "aa": self.in_place,
                        "nconsm": len(self.scheme.consm), "symmetric": self.scheme.stencil.get_symmetric(),
                        "settings": dict(algo.settings) if hasattr(algo, "settings") else None}
             if lowering == "scheme":

@@ -111,6 +111,9 @@ _SIGNATURES = {
                                   c_void_p, c_void_p, c_void_p, c_int, c_int, c_int]),
     "lbm_sim_upload_rows": (c_int, [c_void_p, c_void_p, c_uint64, c_void_p, c_uint64, c_uint64, c_uint64]),
     "lbm_sim_rhs_update": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_double, c_void_p]),
+    "lbm_sim_set_aa": (c_int, [c_void_p, c_void_p]),
+    "lbm_sim_set_bc_odd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "lbm_sim_aa_phase": (c_int, [c_void_p]),
     "lbm_sim_set_scalars": (c_int, [c_void_p, POINTER(c_double), c_int]),
     "lbm_sim_step": (c_int, [c_void_p, c_int]),
     "lbm_sim_boundary_condition": (c_int, [c_void_p]),

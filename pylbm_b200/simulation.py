@@ -37,10 +37,11 @@ from .storage import DeviceArray
 __all__ = ["Simulation", "CudaEngine", "CudaContainer"]
 
 
-def build_kernel_library(scheme, settings=None, storage="f64", need_source=False, compute="f64"):
+def build_kernel_library(scheme, settings=None, storage="f64", need_source=False, compute="f64", aa=False):
     """
     scheme -> per-cell kernel IR -> CUDA C -> liblbmk_<hash>.so (cached in-tree by source hash).
     Needs nvcc but no GPU, so it is also what `__graft_entry__.build()` runs on the build box.
+    `aa`: library for in-place streaming (even / odd step launcher, swapped-read moment kernels).
     Returns (algorithm, library path, CUDA source).
     """
     algo_settings = {"m_local": True, "split": False, "check_isfluid": False}
@@ -48,11 +49,12 @@ def build_kernel_library(scheme, settings=None, storage="f64", need_source=False
     algo = PullAlgorithm(scheme, algo_settings)
     c_storage = "double" if storage == "f64" else "float"
     c_compute = "double" if compute == "f64" else "float"
-    kernels = algo.kernels()
-    path = build.kernel_library_path(kernel_tag(kernels, scheme.dim, algo.ns, storage=c_storage, compute=c_compute))
+    kernels = algo.kernels(aa=aa)
+    path = build.kernel_library_path(kernel_tag(kernels, scheme.dim, algo.ns, storage=c_storage, compute=c_compute,
+                                                aa=aa))
     if os.path.exists(path) and not need_source:
         return algo, path, None          # cached: no lowering, no nvcc
-    source, info = generate_source(kernels, scheme.dim, algo.ns, storage=c_storage, compute=c_compute)
+    source, info = generate_source(kernels, scheme.dim, algo.ns, storage=c_storage, compute=c_compute, aa=aa)
     return algo, build.build_kernels(source, info["hash"]), source
 
 
@@ -77,7 +79,7 @@ class CudaContainer:
 
     gpu_support = True
 
-    def __init__(self, domain, scheme, sorder=None, storage="f64"):
+    def __init__(self, domain, scheme, sorder=None, storage="f64", in_place=False):
         self.dim = domain.dim
         self.mpi_topo = domain.mpi_topo
         self.nv = int(scheme.stencil.nv_ptr[-1])
@@ -90,7 +92,9 @@ class CudaContainer:
         self.sorder = [i for i in range(self.dim + 1)]
         shape = domain.shape_halo
         self.F = DeviceArray(self.nv, shape, self.vmax, storage, scheme.consm)
-        self.Fnew = DeviceArray(self.nv, shape, self.vmax, storage, scheme.consm)
+        # in-place streaming (AA pattern): ONE population array
+        self.Fnew = self.F if in_place else DeviceArray(self.nv, shape, self.vmax, storage, scheme.consm)
+        self.in_place = bool(in_place)
         self._m = None
         self._storage = storage
         self._shape = shape
@@ -149,8 +153,11 @@ class CudaEngine:
             raise ValueError("compute_dtype='float32' needs dtype='float32' (fp32 storage of the populations)")
         return storage, compute
 
-    def _engine_defaults(self, storage, compute, slab=None, nccl_id=None, gather=None):
+    def _engine_defaults(self, storage, compute, slab=None, nccl_id=None, gather=None, in_place=False):
         self.storage, self.compute = storage, compute
+        self.in_place = bool(in_place)
+        if self.in_place and slab is not None and slab[1] > 1:
+            raise ValueError("in-place streaming (in_place=True) runs on one GPU")
         self.rank, self.nranks = slab if slab is not None else (0, 1)
         self._nccl_id, self._gather = nccl_id, gather
         self._mc_version = -1
@@ -263,8 +270,10 @@ class CudaEngine:
             method.fix_iload()
             method.set_rhs()
             method.prepare_device(F)
-        tasks = self._plan_tasks()
-        masks = self._plan_walls() if tasks is None else [None] * len(self.bc.methods)
+        tasks = None if self.in_place else self._plan_tasks()
+        if self.in_place:
+            self.bc.walls = None
+        masks = self._plan_walls() if (tasks is None and not self.in_place) else [None] * len(self.bc.methods)
         # device methods in application order; the entries a wall plan takes out of a method follow it
         # immediately as a stale-only method (same place in the sequence as in the reference)
         info = []
@@ -309,11 +318,46 @@ class CudaEngine:
                 ptr(tasks["ibc"]), ptr(tasks["entry"]), tasks["ngroups_y"], tasks["ngroups_x"], tasks["tx"]),
                 "lbm_sim_set_tasks")
         self.bc.tasks = None if tasks is None else {k: tasks[k] for k in ("ntasks", "nentries", "nblocks")}
+        if self.in_place:
+            self._enable_in_place()
         if not os.environ.get("PYLBM_B200_HOST_TIME_BC"):
             for method in self.bc.methods:
                 method.prepare_time_bc(self)
         self._time_dependent = any(m.is_time_dependent for m in self.bc.methods)
         self._need_init = False
+
+    def _enable_in_place(self):
+        """in-place streaming: the lists of the odd steps (boundary.plan_aa) and the even / odd launcher."""
+        from .boundary import plan_aa
+
+        lib = rt.lib()
+        info = []
+        for method in self.bc.methods:
+            store, l0, l1, _, _, _, _ = method._keep
+            info.append({"store": store, "loads": [l0] + ([l1] if l1 is not None else [])})
+        odd = plan_aa(info, self.container.F, self.scheme.stencil.get_all_velocities(),
+                      self.scheme.stencil.get_symmetric())
+        if odd is None:
+            raise NotImplementedError("in-place streaming: a boundary entry touches the outermost ghost layer "
+                                      "against its own velocity")
+        self._odd_keep = []
+        for method, lists in zip(self.bc.methods, odd):
+            st = np.ascontiguousarray(lists["store"], dtype=np.int64)
+            ld = [np.ascontiguousarray(l, dtype=np.int64) for l in lists["loads"]]
+            self._odd_keep.append((st, ld))
+            rt.check(lib.lbm_sim_set_bc_odd(self._handle, method.device_index, st.ctypes.data, ld[0].ctypes.data,
+                                            ld[1].ctypes.data if len(ld) > 1 else None), "lbm_sim_set_bc_odd")
+        rt.check(lib.lbm_sim_set_aa(self._handle, self.kernels.address("one_time_step_aa")), "lbm_sim_set_aa")
+
+    @property
+    def _swapped(self):
+        """the in-place array is in the swapped layout (an odd number of steps since the last even one)."""
+        return bool(self.in_place and self._handle and rt.lib().lbm_sim_aa_phase(self._handle) == 1)
+
+    def _need_natural(self, what):
+        if self._swapped:
+            raise RuntimeError("in-place streaming: %s needs the natural layout of the populations, i.e. an even "
+                               "number of time steps" % what)
 
     def _plan_tasks(self):
         """boundary entries evaluated by the fused kernel itself (boundary.plan_tasks): one launch per
@@ -388,7 +432,8 @@ class CudaEngine:
             self.m2f()
         else:
             self.f2m()
-        self.container.Fnew.copy_from(self.container.F)
+        if self.container.Fnew is not self.container.F:
+            self.container.Fnew.copy_from(self.container.F)
         self._invalidate_ghosts()
         self._update_m = True
         self.container.release_m()   # rebuilt on demand by f2m; frees nv * cells * 8 bytes of HBM
@@ -432,6 +477,9 @@ class CudaEngine:
             rt.check(rt.lib().lbm_sim_invalidate_ghosts(self._handle), "lbm_sim_invalidate_ghosts")
 
     def f2m(self, **kwargs):
+        if self._swapped:      # interior cells, read through the swapped layout
+            self._launch("f2m_sw", self.container.F, self.container.m, inner=True)
+            return
         self._launch("f2m", self.container.F, self.container.m)
 
     def m2f(self, m_user=None, f_user=None, **kwargs):
@@ -443,6 +491,7 @@ class CudaEngine:
             self._launch("m2f", dm, df, kernels=self._kernels_f64())
             f_user.array[...] = df.get().reshape(f_user.array.shape)
             return
+        self._need_natural("m2f")
         self._launch("m2f", self.container.m, self.container.F)
         self._invalidate_ghosts()
 
@@ -470,6 +519,8 @@ class CudaEngine:
         simulation.py:322-327, and what the reference's NumPy backend does; its Cython backend leaves
         the result in Fnew, base.py:289-296)."""
         F, Fnew = self.container.F, self.container.Fnew
+        if Fnew is F:
+            raise NotImplementedError("the stand-alone transport needs two arrays (in_place=False)")
         self._launch("transport", F, Fnew, inner=True)
         F.copy_from(Fnew)
         self._invalidate_ghosts()
@@ -485,7 +536,10 @@ class CudaEngine:
         (nconsm instead of Q rows of device memory and of store traffic)."""
         c = self.container
         if self._mc_version != self._f_version:
-            self._launch("f2m_consm", c.F, c.mc)
+            if self._swapped:
+                self._launch("f2m_consm_sw", c.F, c.mc, inner=True)
+            else:
+                self._launch("f2m_consm", c.F, c.mc)
             self._mc_version = self._f_version
         return c.mc._in(key)
 
@@ -524,9 +578,11 @@ class CudaEngine:
     @property
     def F_halo(self):
         def get(self_, i):
+            self_._need_natural("F_halo")
             return self_.container.F[i]
 
         def put(self_, i, value):
+            self_._need_natural("writing F")
             self_._update_m = True
             self_.container.F[i] = value
             self_._invalidate_ghosts()
@@ -535,7 +591,19 @@ class CudaEngine:
 
     @property
     def F(self):
-        return _ItemProperty(self, lambda self_, i: self_.container.F._in(i))
+        def get(self_, i):
+            if not self_._swapped:
+                return self_.container.F._in(i)
+            # swapped in-place array: population k of cell x sits in slot (kbar, x + v_k)
+            F = self_.container.F
+            k = int(F._key(i))
+            sym = self_.scheme.stencil.get_symmetric()
+            v = self_.scheme.stencil.get_all_velocities()[k]
+            whole = F.get(int(sym[k]), 1)[0]
+            sl = tuple(slice(w + int(v[d]), whole.shape[d] - w + int(v[d])) for d, w in enumerate(F.vmax))
+            return whole[sl].copy()
+
+        return _ItemProperty(self, get)
 
     # ---- time stepping ------------------------------------------------------
     def _push_scalars(self):
@@ -623,6 +691,8 @@ class Simulation(CudaEngine):
     dtype='float32') also runs the time-step kernels in fp32 arithmetic: the all-single-precision
     mode, tolerance stated in tests/test_gpu_parity.py; moments (`sol.m`), initialisation and wall
     equilibria are always computed in fp64.
+    `in_place=True` selects in-place streaming (AA pattern): ONE population array instead of two -- half
+    the HBM footprint, same traffic per step, bit-identical results (tests/test_gpu_aa.py); single GPU.
     `slab=(rank, nranks)` + `nccl_id` run this process as one x-slab of a multi-GPU run (NCCL
     send/recv halo).  `gather(bytes) -> [bytes of every rank]` (an all-gather provided by the caller,
     e.g. torch.distributed.all_gather_object) additionally enables the direct NVLink halo: the fused
@@ -630,7 +700,7 @@ class Simulation(CudaEngine):
     """
 
     def __init__(self, dico, sorder=None, dtype="float64", check_inverse=False, initialize=True,
-                 slab=None, nccl_id=None, gather=None, compute_dtype=None):
+                 slab=None, nccl_id=None, gather=None, compute_dtype=None, in_place=False):
         generator = str(dico.get("generator", "cuda")).upper()
         if generator != "CUDA":
             raise ValueError(
@@ -638,7 +708,7 @@ class Simulation(CudaEngine):
             )
         rt.ensure_gpu()
         storage, compute = self._storage_names(dtype, compute_dtype)
-        self._engine_defaults(storage, compute, slab, nccl_id, gather)
+        self._engine_defaults(storage, compute, slab, nccl_id, gather, in_place)
 
         rank, nranks = slab if slab is not None else (0, 1)
         topo = None
@@ -664,7 +734,8 @@ class Simulation(CudaEngine):
         codegen_opt = dico.get("codegen_option", None)
         want_source = bool(dico.get("show_code", False) or (codegen_opt and codegen_opt.get("directory")))
         self.algo, lib_path, source = build_kernel_library(self.scheme, user_algo.get("settings", {}), storage,
-                                                           need_source=want_source, compute=compute)
+                                                           need_source=want_source, compute=compute,
+                                                           aa=self.in_place)
         if dico.get("show_code", False):
             print(source)
         if codegen_opt and codegen_opt.get("directory"):
@@ -677,7 +748,7 @@ class Simulation(CudaEngine):
         self.generator = types.SimpleNamespace(backend="CUDA", module=self.kernels)
 
         # ---- storage ----------------------------------------------------
-        self.container = CudaContainer(self.domain, self.scheme, sorder, storage)
+        self.container = CudaContainer(self.domain, self.scheme, sorder, storage, self.in_place)
 
         # ---- boundary lists ---------------------------------------------
         self.bc = Boundary(self.domain, self.generator, dico)
@@ -691,4 +762,5 @@ class Simulation(CudaEngine):
             self._initialize()
 
     def _build_kernels(self, storage, compute):
-        return rt.KernelLibrary(build_kernel_library(self.scheme, self._algo_settings, storage, compute=compute)[1])
+        return rt.KernelLibrary(build_kernel_library(self.scheme, self._algo_settings, storage, compute=compute,
+                                                     aa=self.in_place)[1])

@@ -1,0 +1,120 @@
+"""
+In-place streaming (AA pattern, `in_place=True`): ONE population array, even steps gather and scatter
+back, odd steps are local (include/lbm_b200.h: lbm_sim_set_aa; the algorithm is proven against the
+reference order by brute force in tests/test_aa_emulation.py).  On the GPU the populations of the fluid
+cells must be IDENTICAL to the two-array kernel's after an odd and after an even number of steps, on the
+12 parity workloads: single steps, CUDA-graph pairs, a stand-alone boundary_condition(), time-dependent
+boundary values, periodic boxes, two ghost layers, obstacles.
+"""
+import numpy as np
+import pytest
+
+from conftest import PARITY_CASES, case_id
+
+pytestmark = pytest.mark.gpu
+IDS = [case_id(*c) for c in PARITY_CASES]
+
+
+def _fluid(sim):
+    inner = tuple(slice(v, -v) for v in sim.domain.stencil.vmax)
+    return sim.domain.in_or_out[inner] == sim.domain.valin
+
+
+def _compare(a, b):
+    """a: in-place simulation, b: two-array simulation, same number of steps."""
+    fluid = _fluid(b)
+    for k in range(b.container.nv):
+        fa, fb = a.F[k], b.F[k]
+        assert np.array_equal(fa[fluid], fb[fluid]), "population %d" % k
+    for key in b.scheme.consm:
+        ma, mb = a.m[key], b.m[key]
+        np.testing.assert_allclose(ma[fluid], mb[fluid], rtol=1e-14, atol=1e-300)
+
+
+@pytest.mark.parametrize("name,kw", PARITY_CASES, ids=IDS)
+def test_in_place_streaming_is_bit_identical_to_two_arrays(name, kw):
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    a = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw), in_place=True)
+    b = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw))
+    assert a.container.Fnew is a.container.F and b.container.Fnew is not b.container.F
+    assert a.bc.walls is None
+    for sim in (a, b):
+        for _ in range(3):
+            sim.one_time_step()
+    assert a._swapped
+    _compare(a, b)                      # odd: read through the swapped layout
+    for sim in (a, b):
+        sim.run(4)                      # swapped start: one single step, a graph pair, one single step
+    assert a._swapped and a.nt == 7
+    _compare(a, b)
+    for sim in (a, b):
+        sim.boundary_condition()        # stand-alone, on the odd-step lists
+        sim.one_time_step()
+    assert not a._swapped
+    _compare(a, b)                      # even: natural layout
+    inner = (slice(None),) + tuple(slice(v, -v) for v in a.domain.stencil.vmax)
+    fluid = _fluid(b)
+    assert np.array_equal(a.container.F.get()[inner][:, fluid], b.container.F.get()[inner][:, fluid])
+    for sim in (a, b):
+        sim.boundary_condition()
+        sim.run(6)
+    _compare(a, b)
+    with pytest.raises(NotImplementedError):
+        a.transport()
+
+
+@pytest.mark.parametrize("name,kw", [PARITY_CASES[i] for i in (1, 4, 5)], ids=[IDS[i] for i in (1, 4, 5)])
+@pytest.mark.parametrize("compute", [None, "float32"])
+def test_in_place_streaming_with_fp32_populations(name, kw, compute):
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    a = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw), dtype="float32", compute_dtype=compute, in_place=True)
+    b = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw), dtype="float32", compute_dtype=compute)
+    for sim in (a, b):
+        sim.run(9)
+    _compare(a, b)
+    for sim in (a, b):
+        sim.one_time_step()
+    _compare(a, b)
+
+
+def test_outside_writes_need_the_natural_layout():
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    sim = pylbm_b200.Simulation(cases.karman_d2q9(nx=64, ny=32, perturb=0), in_place=True)
+    sim.one_time_step()
+    with pytest.raises(RuntimeError):
+        sim.F_halo[0] = sim.F[0]
+    with pytest.raises(RuntimeError):
+        sim.m2f()
+    sim.one_time_step()
+    f0 = sim.F_halo[0]
+    sim.F_halo[0] = f0                  # even: allowed, ghosts are refreshed by the next step
+    ref = pylbm_b200.Simulation(cases.karman_d2q9(nx=64, ny=32, perturb=0))
+    ref.run(2)
+    sim.run(3)
+    ref.run(3)
+    _compare(sim, ref)
+
+
+def test_in_place_streaming_through_pylbm_simulation(pylbm):
+    """the north-star interface: `dico['cuda_option'] = {'in_place': True}`."""
+    from pylbm_b200 import cases, plugin
+
+    plugin.register()
+    d = cases.lid_cavity_d3q19(n=16, perturb=0, mod=pylbm, generator="cuda")
+    d["cuda_option"] = {"in_place": True}
+    a = pylbm.Simulation(d)
+    b = pylbm.Simulation(cases.lid_cavity_d3q19(n=16, perturb=0, mod=pylbm, generator="cuda"))
+    assert a.container.Fnew is a.container.F
+    for sim in (a, b):
+        for _ in range(5):
+            sim.one_time_step()
+    _compare(a, b)
+    for sim in (a, b):
+        sim.one_time_step()
+    _compare(a, b)
