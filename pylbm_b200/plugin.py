@@ -553,7 +553,10 @@ def register():
                 raise ValueError("cuda_option['lowering']='scheme' only knows the stock PullAlgorithm")
             if self.in_place and lowering != "scheme":
                 raise NotImplementedError("in-place streaming is generated by the scheme lowering only")
-            context = {"storage": self.storage, "compute": self.compute, "lowering": lowering, "aa": self.in_place,
+            import os
+
+            context = {"storage": self.storage, "compute": self.compute, "lowering": lowering,
+                       "aa": self.in_place or bool(os.environ.get("PYLBM_B200_AA_LIBRARY")),
                        "nconsm": len(self.scheme.consm), "symmetric": self.scheme.stencil.get_symmetric(),
                        "settings": dict(algo.settings) if hasattr(algo, "settings") else None}
             if lowering == "scheme":

@@ -733,9 +733,13 @@ class Simulation(CudaEngine):
         user_algo = dico.get("lbm_algorithm", None) or {}
         codegen_opt = dico.get("codegen_option", None)
         want_source = bool(dico.get("show_code", False) or (codegen_opt and codegen_opt.get("directory")))
+        # (PYLBM_B200_AA_LIBRARY=1: a two-array run on the library generated for in-place streaming, so that
+        # both variants come from ONE lowering -- sympy.cse groups sums differently from call to call, which
+        # moves last bits between separately generated libraries)
+        self._aa_library = self.in_place or bool(os.environ.get("PYLBM_B200_AA_LIBRARY"))
         self.algo, lib_path, source = build_kernel_library(self.scheme, user_algo.get("settings", {}), storage,
                                                            need_source=want_source, compute=compute,
-                                                           aa=self.in_place)
+                                                           aa=self._aa_library)
         if dico.get("show_code", False):
             print(source)
         if codegen_opt and codegen_opt.get("directory"):
@@ -763,4 +767,4 @@ class Simulation(CudaEngine):
 
     def _build_kernels(self, storage, compute):
         return rt.KernelLibrary(build_kernel_library(self.scheme, self._algo_settings, storage, compute=compute,
-                                                     aa=self.in_place)[1])
+                                                     aa=self._aa_library)[1])

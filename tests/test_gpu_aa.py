@@ -15,6 +15,14 @@ pytestmark = pytest.mark.gpu
 IDS = [case_id(*c) for c in PARITY_CASES]
 
 
+@pytest.fixture(autouse=True)
+def one_lowering(monkeypatch):
+    """both variants run kernels of ONE generated library (the one that also holds the in-place
+    launchers): separately generated libraries of the same scheme differ in how sympy.cse groups the
+    sums, i.e. in last bits; against the standard library the agreement is 1e-13 (checked below)."""
+    monkeypatch.setenv("PYLBM_B200_AA_LIBRARY", "1")
+
+
 def _fluid(sim):
     inner = tuple(slice(v, -v) for v in sim.domain.stencil.vmax)
     return sim.domain.in_or_out[inner] == sim.domain.valin
@@ -118,3 +126,28 @@ def test_in_place_streaming_through_pylbm_simulation(pylbm):
     for sim in (a, b):
         sim.one_time_step()
     _compare(a, b)
+
+
+def test_in_place_streaming_against_the_standard_library_and_the_oracle(monkeypatch):
+    """in place (its own library) vs the standard two-array library vs the oracle: 1e-12 of max|field|."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+    from oracle.lbm_oracle import OracleSimulation
+
+    monkeypatch.delenv("PYLBM_B200_AA_LIBRARY", raising=False)
+    name, kw = PARITY_CASES[5]
+    a = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw), in_place=True)
+    b = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw))
+    ora = OracleSimulation(cases.CASES[name](perturb=0, **kw))
+    for nsteps in (25, 1):
+        a.run(nsteps)
+        b.run(nsteps)
+        for _ in range(nsteps):
+            ora.one_time_step()
+        fluid = _fluid(b)
+        for key in b.scheme.consm:
+            okey = [k for k in ora.scheme.consm if str(k) == str(key)][0]
+            want = ora.m[okey][fluid]
+            scale = np.abs(want).max()
+            assert np.abs(a.m[key][fluid] - want).max() <= 1e-12 * scale
+            assert np.abs(a.m[key][fluid] - b.m[key][fluid]).max() <= 1e-13 * scale

@@ -18,5 +18,6 @@ except Exception as exc:
 PY
 }
 run c4_in_place X=1 --in-place --steps 30
-run c4_two_arrays X=1 --steps 30
-nvidia-smi --query-gpu=memory.used --format=csv | tail -1
+run c5_in_place X=1 --in-place --workload d3q27_channel_512x256x256 --steps 40
+run c2_in_place X=1 --in-place --workload d2q9_karman_4096x1024 --steps 400
+run c3_in_place X=1 --in-place --workload d2q4x3_shallow_water_4096 --steps 100
