@@ -72,7 +72,65 @@ class CudaPrinter(C99CodePrinter):
         return "pow%s(%s, %s)" % (self._sfx, self._print(base), self._print(exp))
 
 
+class ExplicitPrinter(CudaPrinter):
+    """Sums and products as explicit round-to-nearest intrinsics: `fma(a, b, acc)` for every product term
+    of a sum, `__dadd_rn` / `__dmul_rn` otherwise.  nvcc can then neither contract nor leave uncontracted
+    anything on its own, so every instantiation of a kernel (two-array, walls, in-place even / odd step)
+    performs bit for bit the same arithmetic -- with the infix form the even-step instantiation of the
+    D3Q19 kernel came out with 4 of its 19 outputs contracted differently (last-bit differences).  The
+    dependency chains are the ones of the infix form (left to right).  Used by the libraries generated
+    for in-place streaming."""
+
+    def __init__(self, single=False):
+        super().__init__(single)
+        self._fma = "__fmaf_rn" if single else "__fma_rn"
+        self._mul = "__fmul_rn" if single else "__dmul_rn"
+        self._add = "__fadd_rn" if single else "__dadd_rn"
+
+    def _product(self, factors):
+        text = self._print(factors[0])
+        for f in factors[1:]:
+            text = "%s(%s, %s)" % (self._mul, text, self._print(f))
+        return text
+
+    def _print_Mul(self, expr):
+        coeff, factors = expr.as_coeff_mul()
+        factors = list(factors)
+        if not factors:
+            return self._print(coeff)
+        if coeff == 1:
+            return self._product(factors)
+        if coeff == -1:
+            return "(-%s)" % self._product(factors)
+        return "%s(%s, %s)" % (self._mul, self._literal(float(sp.Float(coeff, 30))), self._product(factors))
+
+    def _print_Add(self, expr):
+        terms = self._as_ordered_terms(expr, order=None)
+        acc = self._print(terms[0])
+        for term in terms[1:]:
+            coeff, factors = term.as_coeff_mul()
+            factors = list(factors)
+            if not factors:                                   # a number
+                acc = "%s(%s, %s)" % (self._add, acc, self._print(term))
+            elif len(factors) == 1 and coeff == 1:
+                acc = "%s(%s, %s)" % (self._add, acc, self._print(factors[0]))
+            elif len(factors) == 1 and coeff == -1:
+                acc = "%s(%s, -%s)" % (self._add, acc, self._print(factors[0]))
+            elif len(factors) == 1:
+                acc = "%s(%s, %s, %s)" % (self._fma, self._literal(float(sp.Float(coeff, 30))),
+                                          self._print(factors[0]), acc)
+            else:
+                head = self._product(factors[:-1])
+                if coeff == -1:
+                    head = "(-%s)" % head
+                elif coeff != 1:
+                    head = "%s(%s, %s)" % (self._mul, self._literal(float(sp.Float(coeff, 30))), head)
+                acc = "%s(%s, %s, %s)" % (self._fma, head, self._print(factors[-1]), acc)
+        return acc
+
+
 _printers = {False: CudaPrinter(False), True: CudaPrinter(True)}
+_explicit_printers = {False: ExplicitPrinter(False), True: ExplicitPrinter(True)}
 
 
 def _to_exact(expr):
@@ -629,7 +687,7 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
     the kernel body (double, or float for the all-fp32 mode of the fused kernel); `cpt` the number of
     cells a thread of the fused kernel computes."""
     temps, outs = lower_statements(ir.statements, ir.outputs, cse=cse)
-    pr = _printers[compute == "float"]
+    pr = (_explicit_printers if (aa and images) else _printers)[compute == "float"]
     nq = len(ir.in_syms)
     tin = "real_m" if ir.in_array == "m" else "real_f"
     tout = "real_m" if ir.out_array == "m" else "real_f"
@@ -638,9 +696,18 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
     body = ["    const real_c %s = %s;" % (lhs, pr.doprint(rhs)) for lhs, rhs in temps]
     vels = [tuple(-o for o in _canonical(off)) for off in ir.in_offsets]
     if images:
+        if aa:
+            # a library for in-place streaming evaluates every output in the straight-line body, before any
+            # store: the even-step, odd-step and two-array instantiations then contract the same a*b+c into
+            # FMAs (with the expression inside the store blocks nvcc contracted 4 of the 19 D3Q19 outputs
+            # differently in the even-step instantiation: last-bit differences), so they are bit-identical
+            body = body + ["    const real_c o%d_v = %s;" % (k, pr.doprint(o)) for k, o in enumerate(outs)]
+            out_text = ["o%d_v" % k for k in range(len(outs))]
+        else:
+            out_text = [pr.doprint(o) for o in outs]
         stores = [
             "    { const %s o_ = (%s)(%s); %s* p_ = (%s*)(pout + offs.out[%d]); __stcg(p_, o_);%s }"
-            % (tout, tout, pr.doprint(o), tout, tout, k, _inline_image(vels[k], k, slab, tout))
+            % (tout, tout, out_text[k], tout, tout, k, _inline_image(vels[k], k, slab, tout))
             for k, o in enumerate(outs)
         ]
         parts = [_SMEM_DECL]
