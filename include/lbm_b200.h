@@ -179,6 +179,10 @@ int lbm_sim_set_tasks(lbm_sim* sim, lbmk_launch_tasks_fn launcher, int64_t ntask
 int lbm_sim_set_aa(lbm_sim* sim, lbmk_launch_aa_fn launcher);
 int lbm_sim_set_bc_odd(lbm_sim* sim, int ibc, const int64_t* istore, const int64_t* iload0, const int64_t* iload1);
 int lbm_sim_aa_phase(lbm_sim* sim);
+/* in-place streaming with the bounce-back walls of the fastest axis applied by the kernels
+ * (lbmk_one_time_step_aa_walls); the replaced entries stay registered as stale-only methods, with their
+ * odd-step lists, exactly as for lbm_sim_set_walls.  After lbm_sim_set_aa. */
+int lbm_sim_set_aa_walls(lbm_sim* sim, lbmk_launch_aa_walls_fn launcher, const lbmk_walls* walls);
 /* Merged launches: the registered methods [group_ptr[g], group_ptr[g+1]) run as ONE kernel launch.
  * The caller must have proved that, inside a group, no entry reads or overwrites a position that an
  * entry of ANOTHER method of the group stores (results are then bit-identical to running the methods

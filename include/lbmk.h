@@ -154,6 +154,15 @@ int lbmk_one_time_step_tasks(const void* fin, void* fout, const lbmk_grid* g, co
  */
 typedef int (*lbmk_launch_aa_fn)(void* f, const lbmk_grid* g, const double* scalars, int phase, void* stream);
 int lbmk_one_time_step_aa(void* f, const lbmk_grid* g, const double* scalars, int phase, void* stream);
+typedef int (*lbmk_launch_aa_walls_fn)(void* f, const lbmk_grid* g, const double* scalars, int phase,
+                                       const lbmk_walls* walls, void* stream);
+/* in-place steps with the walls of the fastest axis applied by the kernel: the odd step stores the bounced
+ * values into the wall's ghost cells like lbmk_one_time_step_walls, the even step into the cell's OWN slot
+ * of the population moving towards the wall (where the following odd step reads what enters from the wall) */
+int lbmk_one_time_step_aa_walls(void* f, const lbmk_grid* g, const double* scalars, int phase,
+                                const lbmk_walls* walls, void* stream);
+int lbmk_f2m_sw(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
+int lbmk_f2m_consm_sw(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_transport(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 int lbmk_f2m(const void* fin, void* fout, const lbmk_grid* g, const double* scalars, void* stream);
 /* conserved moments only: fout has nconsm populations (rows 0..nconsm-1 of M f), same grid */

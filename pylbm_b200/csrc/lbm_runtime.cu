@@ -618,6 +618,8 @@ struct lbm_sim {
     lbmk_walls walls;
     lbmk_launch_aa_fn aa_fn = nullptr;            // in-place streaming: ONE array, even / odd steps
     int aa_swapped = 0;                           // the array is in the swapped layout (after an even step)
+    lbmk_launch_aa_walls_fn aa_walls_fn = nullptr;   // in-place steps that also apply the fused walls
+    int aa_even_walled = 0;                       // the last even step stored the wall values itself
     lbmk_launch_tasks_fn tasks_fn = nullptr;      // fused kernel evaluates the boundary entries itself
     lbmk_tasks tasks;                             // device arrays owned by this object
     double* scratch = nullptr;
@@ -960,6 +962,25 @@ extern "C" int lbm_sim_set_aa(lbm_sim* s, lbmk_launch_aa_fn launcher) {
     return 0;
 }
 
+extern "C" int lbm_sim_set_aa_walls(lbm_sim* s, lbmk_launch_aa_walls_fn launcher, const lbmk_walls* walls) {
+    if (!s) return ARG_ERROR("null sim");
+    if (!s->aa_fn) return ARG_ERROR("lbm_sim_set_aa_walls: call lbm_sim_set_aa first");
+    if (s->aa_swapped) return ARG_ERROR("lbm_sim_set_aa_walls: the array is in the swapped layout");
+    if (walls && !launcher) return ARG_ERROR("lbm_sim_set_aa_walls: launcher missing");
+    if (walls && !(s->wrap_mask & (1 << 2))) return ARG_ERROR("lbm_sim_set_aa_walls: the fastest axis is not maintained by the kernel");
+    cudaStreamSynchronize(s->stream);
+    drop_graph(s);
+    if (walls) {
+        s->walls = *walls;
+        s->aa_walls_fn = launcher;
+    } else {
+        s->aa_walls_fn = nullptr;
+    }
+    s->aa_even_walled = 0;
+    s->ghost_fresh = 0;
+    return 0;
+}
+
 extern "C" int lbm_sim_aa_phase(lbm_sim* s) { return !s || !s->aa_fn ? -1 : s->aa_swapped; }
 
 extern "C" int lbm_sim_bc_groups(lbm_sim* s, int ngroups, const int* group_ptr) {
@@ -1152,7 +1173,8 @@ static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
 }
 
 static int apply_bc_method(lbm_sim* s, BcMethod& b, void* f, cudaStream_t st) {
-    if (b.stale_only && s->ghost_fresh) return 0;   // the previous fused launch stored these values
+    // the previous fused launch stored these values (in place: the even step, into the cells' own slots)
+    if (b.stale_only && (s->ghost_fresh || (s->aa_fn && s->aa_swapped && s->aa_even_walled))) return 0;
     const bool odd = s->aa_fn && s->aa_swapped;
     if (odd && b.ncond > 0 && !b.istore_odd) return ARG_ERROR("in-place streaming: odd-step lists missing (lbm_sim_set_bc_odd)");
     const long long* is_ = odd ? b.istore_odd : b.istore;
@@ -1194,7 +1216,8 @@ static int apply_bcs(lbm_sim* s, void* f, cudaStream_t st) {
         segs.total = 0;
         for (int i = lo; i < hi; ++i) {
             BcMethod& b = s->bcs[i];
-            if (b.ncond <= 0 || (b.stale_only && s->ghost_fresh)) continue;
+            if (b.ncond <= 0 || (b.stale_only && (s->ghost_fresh || (s->aa_fn && s->aa_swapped && s->aa_even_walled))))
+                continue;
             BcSegment& sg = segs.seg[segs.n++];
             sg.begin = segs.total;
             sg.kind = b.kind;
@@ -1291,8 +1314,12 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
         }
         lbmk_grid g = s->d.grid;
         g.wrap = s->wrap_mask | (g_pdl ? LBMK_WRAP_PDL : 0);
-        rc = s->aa_fn(f, &g, scal, s->aa_swapped, (void*)st);
+        if (s->aa_walls_fn)
+            rc = s->aa_walls_fn(f, &g, scal, s->aa_swapped, &s->walls, (void*)st);
+        else
+            rc = s->aa_fn(f, &g, scal, s->aa_swapped, (void*)st);
         if (rc) return set_error(rc, "in-place kernel launch", cudaGetErrorString((cudaError_t)(-rc)));
+        s->aa_even_walled = (!s->aa_swapped && s->aa_walls_fn) ? 1 : 0;
         if (ev1) cudaEventRecord(ev1, st);
         s->launches += 1;
         s->aa_swapped ^= 1;

@@ -334,6 +334,7 @@ struct lbmk_offs_%(name)s {
     long long in[%(nin)d];
     long long out[%(nout)d];
     long long wall[%(nout)d];   // fused kernel with walls: store position of the bounced population
+    long long nat[%(nout)d];    // population k of the cell itself (in-place even step with walls)
     unsigned fold;   // 0: blockIdx.y / blockIdx.z are the row group / the index of axis 0; otherwise the
                      // number of row groups per axis-0 index, (z, y) being one linear index (more than
                      // 65535 row groups or planes: e.g. a 2-D lattice with 100 000 rows)
@@ -398,7 +399,7 @@ lbmk_kernel_%(name)s(const %(tin)s* %(restrict)s fin, %(tout)s* %(restrict)s fou
         offs.in[k] = (inpop_[k] * g->pstride + noff[k][0] * plane + noff[k][1] * g->pitch + noff[k][2]) * (long long)sizeof(%(tin)s);
     for (int k = 0; k < %(nout)d; ++k)
         offs.out[k] = k * g->pstride * (long long)sizeof(%(tout)s);
-    for (int k = 0; k < %(nout)d; ++k) offs.wall[k] = 0;
+    for (int k = 0; k < %(nout)d; ++k) { offs.wall[k] = 0; offs.nat[k] = offs.out[k]; }
 %(images_launch)s%(kernel_call)s
     return -(int)cudaGetLastError();
 }
@@ -569,7 +570,12 @@ def _inline_image(v, k, slab, tout):
     wall, neg = ("wlo", "walls.neg_lo") if v[2] < 0 else ("whi", "walls.neg_hi")
     bounce = (" if (%s) __stcg((%s*)(pout + offs.wall[%d]), (%s)__dadd_rn(%s ? -(double)o_ : (double)o_, walls.rhs[%d]));"
               % (wall, tout, k, tout, neg, k))
-    return aa + " if (!AAEVEN) { if (!WALLZ) {%s } else {%s } }" % (image, bounce)
+    # in-place even step with walls: the bounced value goes into the cell's OWN slot of population k --
+    # where the odd step reads the population entering from the wall (the transformed position of the
+    # list entry (sym k, c + v_k) is (k, c)); that slot belongs to the ghost cell c + v_k in this step
+    own = (" if (%s) __stcg((%s*)(pout + offs.nat[%d]), (%s)__dadd_rn(%s ? -(double)o_ : (double)o_, walls.rhs[%d]));"
+           % (wall, tout, k, tout, neg, k))
+    return aa + " if (!AAEVEN) { if (!WALLZ) {%s } else {%s } } else if (WALLZ) {%s }" % (image, bounce, own)
 
 
 def _images_code(velocities, tout, slab):
@@ -616,6 +622,12 @@ _LAUNCH_TAIL_AA = """
 extern "C" int lbmk_%(name)s_aa(void* f, const lbmk_grid* g, const double* scalars, int phase, void* stream)
 {
     return lbmk_launch_%(name)s_(f, f, g, scalars, nullptr, nullptr, nullptr, stream, phase ? 2 : 1);
+}
+// the same with the bounce-back walls of the fastest axis applied by the kernel (walls may be NULL)
+extern "C" int lbmk_%(name)s_aa_walls(void* f, const lbmk_grid* g, const double* scalars, int phase,
+                                      const lbmk_walls* walls, void* stream)
+{
+    return lbmk_launch_%(name)s_(f, f, g, scalars, nullptr, walls, nullptr, stream, phase ? 2 : 1);
 }
 """
 _LAUNCH_TAIL_WALLS = """
@@ -676,7 +688,10 @@ _CALL_WALLS = """    const lbmk_peers pr_ = peers ? *peers : lbmk_peers{nullptr,
     else
         cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<0, false>,
             (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, lbmk_walls{}, notasks_%(scalar_args)s);"""
-_CALL_AA = """ else if (aa_phase == 1)
+_CALL_AA = """ else if (aa_phase == 1 && walls)
+        cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<3, false>,
+            (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, *walls, notasks_%(scalar_args)s);
+    else if (aa_phase == 1)
         cudaLaunchKernelEx(&cfg_, lbmk_kernel_%(name)s<2, false>,
             (const %(tin)s*)fin, (%(tout)s*)fout, gk_, offs, pr_, img, lbmk_walls{}, notasks_%(scalar_args)s);"""
 
@@ -742,10 +757,11 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
             shifts = []
             for a in range(3):
                 for mag in sorted({abs(v[a]) for v in vels if v[a] != 0}):
-                    shifts.append("    const long long aaP%d_%d = (AAEVEN && i%d + %d >= g.n[%d] - g.w[%d]) ? img.dhigh[%d] : 0LL;"
-                                  % (a, mag, a, mag, a, a, a))
-                    shifts.append("    const long long aaM%d_%d = (AAEVEN && i%d - %d < g.w[%d]) ? img.dlow[%d] : 0LL;"
-                                  % (a, mag, a, mag, a, a))
+                    on = "AAEVEN && !WALLZ" if a == 2 else "AAEVEN"   # walls of the fastest axis: no image
+                    shifts.append("    const long long aaP%d_%d = (%s && i%d + %d >= g.n[%d] - g.w[%d]) ? img.dhigh[%d] : 0LL;"
+                                  % (a, mag, on, a, mag, a, a, a))
+                    shifts.append("    const long long aaM%d_%d = (%s && i%d - %d < g.w[%d]) ? img.dlow[%d] : 0LL;"
+                                  % (a, mag, on, a, mag, a, a))
                     shifts.append("    (void)aaP%d_%d; (void)aaM%d_%d;" % (a, mag, a, mag))
             parts.append(_IMAGES_PROLOGUE % dict(tout=tout, aa_shifts="\n".join(shifts)))
             parts.extend(body)
@@ -784,8 +800,8 @@ def kernel_source(ir, storage="double", cse=True, minblocks=1, images=False, sla
         offset_table=table,
         thread_body=thread_body,
         template="template <int MODE, bool TASKS>\n" if images else "",
-        mode_decl=("    constexpr bool WALLZ = (MODE == 1), AAEVEN = (MODE == 2); (void)WALLZ; (void)AAEVEN;\n"
-                   if images else ""),
+        mode_decl=("    constexpr bool WALLZ = (MODE == 1 || MODE == 3), AAEVEN = (MODE == 2 || MODE == 3); "
+                   "(void)WALLZ; (void)AAEVEN;\n" if images else ""),
         restrict="LBMK_RESTRICT" if images else "__restrict__",
         inpop_table=", ".join(str(int(k)) for k in (getattr(ir, "in_pops", None) or range(nq))),
         peer_param=(", const lbmk_peers pr, const lbmk_images img, const lbmk_walls walls, const lbmk_tasks tasks"

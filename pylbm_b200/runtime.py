@@ -114,6 +114,7 @@ _SIGNATURES = {
     "lbm_sim_set_aa": (c_int, [c_void_p, c_void_p]),
     "lbm_sim_set_bc_odd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "lbm_sim_aa_phase": (c_int, [c_void_p]),
+    "lbm_sim_set_aa_walls": (c_int, [c_void_p, c_void_p, c_void_p]),
     "lbm_sim_set_scalars": (c_int, [c_void_p, POINTER(c_double), c_int]),
     "lbm_sim_step": (c_int, [c_void_p, c_int]),
     "lbm_sim_boundary_condition": (c_int, [c_void_p]),

@@ -271,9 +271,7 @@ class CudaEngine:
             method.set_rhs()
             method.prepare_device(F)
         tasks = None if self.in_place else self._plan_tasks()
-        if self.in_place:
-            self.bc.walls = None
-        masks = self._plan_walls() if (tasks is None and not self.in_place) else [None] * len(self.bc.methods)
+        masks = self._plan_walls() if tasks is None else [None] * len(self.bc.methods)
         # device methods in application order; the entries a wall plan takes out of a method follow it
         # immediately as a stale-only method (same place in the sequence as in the reference)
         info = []
@@ -290,16 +288,18 @@ class CudaEngine:
                                          None, wrhs.ctypes.data, None, 0, None, None)
                 rt.check(idx, "lbm_sim_add_bc(wall entries)")
                 rt.check(lib.lbm_sim_bc_stale_only(self._handle, idx, 1), "lbm_sim_bc_stale_only")
-                self._wall_keep.append((wstore, wl0, wrhs))
+                self._wall_keep.append((wstore, wl0, wrhs, idx))
                 info.append((wstore, [wl0], False))          # never merged with its neighbours
+        walls_desc = None
         if self.bc.walls is not None:
-            w = rt.LbmkWalls()
+            w = walls_desc = rt.LbmkWalls()
             w.lo_plane, w.hi_plane = self.bc.walls["lo_plane"], self.bc.walls["hi_plane"]
             w.neg_lo, w.neg_hi = self.bc.walls["neg_lo"], self.bc.walls["neg_hi"]
             for k in range(64):
                 w.rhs[k] = float(self.bc.walls["rhs"][k])
-            rt.check(lib.lbm_sim_set_walls(self._handle, self.kernels.address("one_time_step_walls"), ctypes.byref(w)),
-                     "lbm_sim_set_walls")
+            if not self.in_place:
+                rt.check(lib.lbm_sim_set_walls(self._handle, self.kernels.address("one_time_step_walls"),
+                                               ctypes.byref(w)), "lbm_sim_set_walls")
         if len(info) > 1:
             # consecutive methods that provably do not interact run as one kernel launch
             from .boundary import merge_groups
@@ -319,35 +319,44 @@ class CudaEngine:
                 "lbm_sim_set_tasks")
         self.bc.tasks = None if tasks is None else {k: tasks[k] for k in ("ntasks", "nentries", "nblocks")}
         if self.in_place:
-            self._enable_in_place()
+            self._enable_in_place(walls_desc)
         if not os.environ.get("PYLBM_B200_HOST_TIME_BC"):
             for method in self.bc.methods:
                 method.prepare_time_bc(self)
         self._time_dependent = any(m.is_time_dependent for m in self.bc.methods)
         self._need_init = False
 
-    def _enable_in_place(self):
-        """in-place streaming: the lists of the odd steps (boundary.plan_aa) and the even / odd launcher."""
+    def _enable_in_place(self, walls_desc=None):
+        """in-place streaming: the lists of the odd steps (boundary.plan_aa) for every registered method --
+        the stale-only wall entries included -- and the even / odd launcher (with the fused walls when a
+        wall plan was accepted)."""
         from .boundary import plan_aa
 
         lib = rt.lib()
-        info = []
+        info, index = [], []
         for method in self.bc.methods:
             store, l0, l1, _, _, _, _ = method._keep
             info.append({"store": store, "loads": [l0] + ([l1] if l1 is not None else [])})
+            index.append(method.device_index)
+        for wstore, wl0, _, idx in self._wall_keep:
+            info.append({"store": wstore, "loads": [wl0]})
+            index.append(idx)
         odd = plan_aa(info, self.container.F, self.scheme.stencil.get_all_velocities(),
                       self.scheme.stencil.get_symmetric())
         if odd is None:
             raise NotImplementedError("in-place streaming: a boundary entry touches the outermost ghost layer "
                                       "against its own velocity")
         self._odd_keep = []
-        for method, lists in zip(self.bc.methods, odd):
+        for idx, lists in zip(index, odd):
             st = np.ascontiguousarray(lists["store"], dtype=np.int64)
             ld = [np.ascontiguousarray(l, dtype=np.int64) for l in lists["loads"]]
             self._odd_keep.append((st, ld))
-            rt.check(lib.lbm_sim_set_bc_odd(self._handle, method.device_index, st.ctypes.data, ld[0].ctypes.data,
+            rt.check(lib.lbm_sim_set_bc_odd(self._handle, idx, st.ctypes.data, ld[0].ctypes.data,
                                             ld[1].ctypes.data if len(ld) > 1 else None), "lbm_sim_set_bc_odd")
         rt.check(lib.lbm_sim_set_aa(self._handle, self.kernels.address("one_time_step_aa")), "lbm_sim_set_aa")
+        if walls_desc is not None:
+            rt.check(lib.lbm_sim_set_aa_walls(self._handle, self.kernels.address("one_time_step_aa_walls"),
+                                              ctypes.byref(walls_desc)), "lbm_sim_set_aa_walls")
 
     @property
     def _swapped(self):

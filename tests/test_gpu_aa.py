@@ -47,7 +47,7 @@ def test_in_place_streaming_is_bit_identical_to_two_arrays(name, kw):
     a = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw), in_place=True)
     b = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw))
     assert a.container.Fnew is a.container.F and b.container.Fnew is not b.container.F
-    assert a.bc.walls is None
+    assert (a.bc.walls is None) == (b.bc.walls is None)      # the fused walls work in place as well
     for sim in (a, b):
         for _ in range(3):
             sim.one_time_step()
@@ -151,3 +151,33 @@ def test_in_place_streaming_against_the_standard_library_and_the_oracle(monkeypa
             scale = np.abs(want).max()
             assert np.abs(a.m[key][fluid] - want).max() <= 1e-12 * scale
             assert np.abs(a.m[key][fluid] - b.m[key][fluid]).max() <= 1e-13 * scale
+
+
+@pytest.mark.parametrize("name,kw", [("lid_cavity_d3q19", dict(n=16)), ("channel_sphere_d3q27", dict(nx=21, ny=13, nz=9)),
+                                     ("heat_d2q5", dict(n=24, plain=True))])
+def test_in_place_streaming_with_and_without_the_fused_walls(name, kw, monkeypatch):
+    """the wall plan (bounce-back walls of the fastest axis applied by the kernels) in place: the even step
+    stores the bounced value into the cell's own slot; populations identical with the plan on and off,
+    also after an outside write (one step through the stale-only entries)."""
+    import pylbm_b200
+    from pylbm_b200 import cases
+
+    def run(walls):
+        if walls:
+            monkeypatch.delenv("PYLBM_B200_NO_WALLS", raising=False)
+        else:
+            monkeypatch.setenv("PYLBM_B200_NO_WALLS", "1")
+        sim = pylbm_b200.Simulation(cases.CASES[name](perturb=0, **kw), in_place=True)
+        assert (sim.bc.walls is not None) == walls
+        sim.run(7)
+        sim.one_time_step()
+        sim.boundary_condition()
+        sim.F_halo[1] = sim.F_halo[1]
+        sim.run(5)
+        return sim
+
+    a, b = run(True), run(False)
+    assert a._swapped and b._swapped
+    fluid = _fluid(b)
+    for k in range(b.container.nv):
+        assert np.array_equal(a.F[k][fluid], b.F[k][fluid]), "population %d" % k

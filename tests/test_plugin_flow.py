@@ -86,3 +86,25 @@ def test_no_gpu_is_an_error_not_a_fallback(pylbm):
     plugin.register()
     with pytest.raises(runtime.LbmError):
         pylbm.Simulation(cases.karman_d2q9(nx=32, ny=16, mod=pylbm, generator="cuda"))
+
+
+def test_in_place_option_registers_odd_lists_and_one_array(cuda_pylbm):
+    """`dico['cuda_option'] = {'in_place': True}`: ONE population array, the odd-step lists of every method
+    and the even / odd launcher are handed to the runtime; a step is still one runtime call."""
+    from pylbm_b200 import cases
+
+    pylbm, fake = cuda_pylbm
+    dico = cases.karman_d2q9(nx=32, ny=16, mod=pylbm, generator="cuda")
+    dico["cuda_option"] = {"in_place": True}
+    sol = pylbm.Simulation(dico)
+    assert sol.container.Fnew is sol.container.F and sol.in_place
+    assert "one_time_step_aa" not in sol.kernels.info["routines"]          # a launcher, not a routine
+    assert {"f2m_sw", "f2m_consm_sw"} <= set(sol.kernels.info["routines"])
+    assert fake.count("lbm_sim_set_bc_odd") == len(sol.bc.methods) and fake.count("lbm_sim_set_aa") == 1
+    assert fake.count("lbm_sim_set_walls") == 0 and fake.count("lbm_sim_set_tasks") == 0
+    before = len(fake.calls)
+    sol.one_time_step()
+    assert [n for n, _ in fake.calls[before:]] == ["lbm_sim_step"]
+    # the odd lists are the even lists moved by (k, y) -> (kbar, y + v_k): same length, all different
+    for method, (store, loads) in zip(sol.bc.methods, sol._odd_keep):
+        assert store.shape == method._keep[0].shape and (store != method._keep[0]).all()

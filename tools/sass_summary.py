@@ -15,7 +15,8 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-DEFAULT = [("lid_cavity_d3q19", dict(n=512), "f64", "f64"), ("lid_cavity_d3q19", dict(n=512), "f32", "f64"),
+DEFAULT = [("lid_cavity_d3q19", dict(n=512), "f64", "f64"), ("lid_cavity_d3q19", dict(n=512), "f64", "f64", True),
+           ("lid_cavity_d3q19", dict(n=512), "f32", "f64"),
            ("lid_cavity_d3q19", dict(n=512), "f32", "f32"), ("karman_d2q9", dict(nx=4096, ny=1024), "f64", "f64"),
            ("channel_sphere_d3q27", dict(nx=512, ny=256, nz=256), "f64", "f64")]
 WATCH = ["LDG", "STG", "DFMA", "DADD", "DMUL", "FFMA", "FADD", "FMUL", "MUFU", "F2F", "IMAD", "IADD3", "LOP3",
@@ -51,20 +52,26 @@ def main():
     from pylbm_b200.scheme import Scheme
     from pylbm_b200.simulation import build_kernel_library
 
-    print("# SASS summary of the fused kernel `lbmk_kernel_one_time_step<WALLZ, TASKS>` (cuobjdump -sass, sm_100a)\n")
+    print("# SASS summary of the fused kernel `lbmk_kernel_one_time_step<MODE, TASKS>` (cuobjdump -sass, sm_100a)\n")
     print("Static instruction counts of the whole kernel body (one thread = one cell; the image tail and the\n"
           "task prologue are rarely executed).  No LDL/STL = no register spills.  Not a tensor-core / TMA kernel by\n"
           "design (every population value is read once: nothing to stage or reuse), so UTCMMA / UTMALDG do not\n"
           "apply; the tells here are coalesced `LDG.E.64.CONSTANT` / `STG.E.64.STRONG.GPU` per population and DFMA.\n")
-    for name, kw, storage, compute in DEFAULT:
+    for entry in DEFAULT:
+        name, kw, storage, compute = entry[:4]
+        aa = len(entry) > 4
         scheme = Scheme(cases.CASES[name](**kw))
-        _, path, _ = build_kernel_library(scheme, storage=storage, compute=compute)
-        print("## %s %s, storage %s, arithmetic %s (`%s`)\n" % (name, kw, storage, compute, os.path.basename(path)))
+        _, path, _ = build_kernel_library(scheme, storage=storage, compute=compute, aa=aa)
+        print("## %s %s, storage %s, arithmetic %s%s (`%s`)\n" % (
+            name, kw, storage, compute, ", library for in-place streaming (explicit FMA lowering)" if aa else "",
+            os.path.basename(path)))
         print("| instantiation | regs | instr | " + " | ".join(WATCH) + " |")
         print("|---|---|---|" + "---|" * len(WATCH))
         for fn, total, counts, variants, regs in summarize(path):
-            tag = re.search(r"ILb(\d)ELb(\d)E", fn)
-            label = "WALLZ=%s TASKS=%s" % (tag.group(1), tag.group(2)) if tag else fn[:40]
+            tag = re.search(r"ILi(\d)ELb(\d)E", fn)
+            modes = {"0": "two arrays", "1": "two arrays + fused walls", "2": "in-place even step",
+                     "3": "in-place even step + fused walls"}
+            label = "%s%s" % (modes.get(tag.group(1), tag.group(1)), ", task table" if tag.group(2) == "1" else "") if tag else fn[:40]
             print("| %s | %s | %d | " % (label, regs or "?", total) + " | ".join(str(counts.get(w, 0)) for w in WATCH) + " |")
             if tag and tag.group(1) == "0" and tag.group(2) == "0":
                 keep = ", ".join("%s x%d" % kv for kv in sorted(variants.items()))
