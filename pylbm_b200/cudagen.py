@@ -303,7 +303,7 @@ typedef %(storage)s real_f;   // storage type of the populations in HBM
 // no non-coherent loads there
 #if %(aa)d
 #define LBMK_RESTRICT
-#define LBMK_LDG(p) (*(p))
+#define LBMK_LDG(p) __ldcg(p)     /* ld.global.cg: a global (not generic) load that is coherent at L2 */
 #else
 #define LBMK_RESTRICT __restrict__
 #define LBMK_LDG(p) __ldg(p)
