@@ -37,6 +37,11 @@ What is restated, with the reference lines it follows:
 The problem description (stencil, M, equilibria, boundary lists) comes from the
 host front-end of the package, which is itself pinned bit-for-bit against the
 reference by the same fixtures.
+
+Since round 2 the unmodified reference itself is a second, fully independent checker:
+tools/make_ref.sh installs it into oracle/_ref/ (git-ignored, travels to the GPU box), where
+tests/test_gpu_plugin.py and tests/test_gpu_standalone.py run its Cython and NumPy generators
+live beside the CUDA path, and bench.py times it as the CPU baseline (kind "reference").
 """
 
 import ctypes
