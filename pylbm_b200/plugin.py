@@ -385,6 +385,11 @@ def _process_group():
     """(slab, nccl_id, gather) of this process."""
     if _config["slab"] is not None:
         return _config["slab"], _config["nccl_id"], (_config["gather"] if _config["halo"] == "peer" else None)
+    import sys
+
+    if "torch" not in sys.modules:
+        # a process group can only exist if the caller imported torch: do not pay its import otherwise
+        return None, None, None
     try:
         import torch.distributed as dist
     except Exception:
@@ -561,6 +566,19 @@ def register():
                        "settings": dict(algo.settings) if hasattr(algo, "settings") else None}
             if lowering == "scheme":
                 context["scheme"] = _scheme_twin(dico, self.scheme)
+                # the scheme lowering does not consume the reference's symbolic routines: building them
+                # (algorithm/base.py:602-628, several seconds of sympy for a 3-D scheme) is deferred until
+                # somebody asks for them (`sol.algo.generate()` still works, `lowering='ir'` runs it)
+                # (the closure must not capture the simulation: a reference cycle would keep its device
+                # arrays alive until the next garbage collection)
+                reference_generate, generator = algo.generate, self.generator
+
+                def generate_routines():
+                    if not generator.routines:
+                        reference_generate()
+
+                algo.generate = lambda: None
+                algo.generate_routines = generate_routines
             self.generator.cuda_context = context
             return algo
 
