@@ -174,8 +174,11 @@ int lbm_sim_set_tasks(lbm_sim* sim, lbmk_launch_tasks_fn launcher, int64_t ntask
  * lbmk_one_time_step_aa of a kernel library generated for it.  Steps alternate between the even kernel
  * (natural -> swapped layout) and the odd kernel (swapped -> natural); after an even step every position
  * (k, y) of a boundary list is found at (kbar, y + v_k), so each method needs its lists once more in that
- * form (lbm_sim_set_bc_odd; boundary.plan_aa computes them).  Single GPU, not combined with
- * lbm_sim_set_walls / lbm_sim_set_tasks.  lbm_sim_aa_phase: 0 natural, 1 swapped, -1 off. */
+ * form (lbm_sim_set_bc_odd; boundary.plan_aa computes them).  On x-slabs (after lbm_sim_comm_init, NCCL
+ * halo, not the peer halo) an even step is followed by a REVERSE exchange: the ghost planes, where the
+ * even kernel deposited what left through the slab faces, travel to the neighbours' interior planes.
+ * Not combined with lbm_sim_set_tasks; fused walls through lbm_sim_set_aa_walls.
+ * lbm_sim_aa_phase: 0 natural, 1 swapped, -1 off. */
 int lbm_sim_set_aa(lbm_sim* sim, lbmk_launch_aa_fn launcher);
 int lbm_sim_set_bc_odd(lbm_sim* sim, int ibc, const int64_t* istore, const int64_t* iload0, const int64_t* iload1);
 int lbm_sim_aa_phase(lbm_sim* sim);

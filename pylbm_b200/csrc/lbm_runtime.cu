@@ -951,9 +951,10 @@ extern "C" int lbm_sim_set_aa(lbm_sim* s, lbmk_launch_aa_fn launcher) {
         return 0;
     }
     if (s->f != s->fnew) return ARG_ERROR("lbm_sim_set_aa: in-place streaming runs on ONE array (desc.f == desc.fnew)");
-    if (s->nranks > 1) return ARG_ERROR("lbm_sim_set_aa: single GPU only");
+    if (s->nranks > 1 && s->peers_ready)
+        return ARG_ERROR("lbm_sim_set_aa: on several GPUs in-place streaming uses the NCCL halo, not the peer halo");
     if (s->walls_fn || s->tasks_fn) return ARG_ERROR("lbm_sim_set_aa: not combined with lbm_sim_set_walls / lbm_sim_set_tasks");
-    if (s->wrap_mask != s->d.periodic_mask)
+    if ((s->wrap_mask | (s->nranks > 1 ? (1 << s->slab_axis) : 0)) != s->d.periodic_mask)
         return ARG_ERROR("lbm_sim_set_aa: the fused kernel must maintain the images of every ghost axis "
                          "(an axis is shorter than four ghost widths, or PYLBM_B200_NO_WRAP is set)");
     s->aa_fn = launcher;
@@ -1118,7 +1119,7 @@ static cudaError_t launch_planes(lbm_sim* s, void* f, void* buf, int side_bit, l
     return cudaGetLastError();
 }
 
-static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
+static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st, bool reverse = false) {
     // planes [w, 2w) go to the left neighbour's right ghost, planes [n-2w, n-w) to the right
     // neighbour's left ghost (periodic ring, like the reference's Cartesian communicator).  Only the
     // populations that enter the neighbour through that face travel (sign-matched, PopSel), packed into
@@ -1140,10 +1141,17 @@ static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
         if (sel.side[i] & 2) ++n_neg;
         if (sel.side[i] & 1) ++n_pos;
     }
-    // buffers: [0] send to the left (neg), [1] send to the right (pos), [2] recv from the right (neg),
-    // [3] recv from the left (pos)
-    const size_t need[4] = {(size_t)n_neg * count * esz, (size_t)n_pos * count * esz,
-                            (size_t)n_neg * count * esz, (size_t)n_pos * count * esz};
+    // REVERSE exchange (in-place streaming, after an even step): the ghost planes, where the even kernel
+    // deposited the populations that left through the slab faces, travel to the neighbours' interior
+    // planes -- the low ghost layer holds the slots of the populations moving in +axis, and it goes to the
+    // LEFT neighbour's planes [n-2w, n-w); the high one (-axis) to the right neighbour's planes [w, 2w).
+    const int bit_left = reverse ? 1 : 2, bit_right = reverse ? 2 : 1;        // populations sent left / right
+    const int n_left = reverse ? n_pos : n_neg, n_right = reverse ? n_neg : n_pos;
+    const long long src_left = reverse ? 0 : (long long)w, src_right = reverse ? n - w : n - 2 * w;
+    const long long dst_from_right = reverse ? n - 2 * w : n - w, dst_from_left = reverse ? (long long)w : 0;
+    // buffers: [0] send to the left, [1] send to the right, [2] recv from the right, [3] recv from the left
+    const size_t need[4] = {(size_t)n_left * count * esz, (size_t)n_right * count * esz,
+                            (size_t)n_left * count * esz, (size_t)n_right * count * esz};
     for (int i = 0; i < 4; ++i) {
         if (need[i] > s->xbuf_bytes[i]) {
             if (s->xbuf[i]) cudaFree(s->xbuf[i]);
@@ -1153,21 +1161,22 @@ static int exchange_slabs(lbm_sim* s, void* f, cudaStream_t st) {
             s->xbuf_bytes[i] = need[i];
         }
     }
-    cudaError_t e = launch_planes(s, f, s->xbuf[0], 2, g.lead + (long long)w * stride, count, n_neg, 1, st);
-    if (e == cudaSuccess) e = launch_planes(s, f, s->xbuf[1], 1, g.lead + (n - 2 * w) * stride, count, n_pos, 1, st);
+    cudaError_t e = launch_planes(s, f, s->xbuf[0], bit_left, g.lead + src_left * stride, count, n_left, 1, st);
+    if (e == cudaSuccess) e = launch_planes(s, f, s->xbuf[1], bit_right, g.lead + src_right * stride, count, n_right, 1, st);
     if (e != cudaSuccess) return set_error(-(int)e, "halo pack", cudaGetErrorString(e));
     NCCL_TRY(g_nccl.GroupStart());
     // receives first from the right, then from the left: with 2 ranks both neighbours are the same peer
-    // and messages are matched in posting order
-    if (n_neg) NCCL_TRY(g_nccl.Recv(s->xbuf[2], (size_t)n_neg * count, dtype, right, s->comm, st));
-    if (n_pos) NCCL_TRY(g_nccl.Recv(s->xbuf[3], (size_t)n_pos * count, dtype, left, s->comm, st));
-    if (n_neg) NCCL_TRY(g_nccl.Send(s->xbuf[0], (size_t)n_neg * count, dtype, left, s->comm, st));
-    if (n_pos) NCCL_TRY(g_nccl.Send(s->xbuf[1], (size_t)n_pos * count, dtype, right, s->comm, st));
+    // and messages are matched in posting order (what the right neighbour sends to ITS left is what it
+    // packed with bit_left)
+    if (n_left) NCCL_TRY(g_nccl.Recv(s->xbuf[2], (size_t)n_left * count, dtype, right, s->comm, st));
+    if (n_right) NCCL_TRY(g_nccl.Recv(s->xbuf[3], (size_t)n_right * count, dtype, left, s->comm, st));
+    if (n_left) NCCL_TRY(g_nccl.Send(s->xbuf[0], (size_t)n_left * count, dtype, left, s->comm, st));
+    if (n_right) NCCL_TRY(g_nccl.Send(s->xbuf[1], (size_t)n_right * count, dtype, right, s->comm, st));
     NCCL_TRY(g_nccl.GroupEnd());
     s->launches += 1;
-    // the high ghost layer is only read for populations moving in -axis, the low one for +axis
-    e = launch_planes(s, f, s->xbuf[2], 2, g.lead + (n - w) * stride, count, n_neg, 0, st);
-    if (e == cudaSuccess) e = launch_planes(s, f, s->xbuf[3], 1, g.lead, count, n_pos, 0, st);
+    // forward: the high ghost layer is only read for populations moving in -axis, the low one for +axis
+    e = launch_planes(s, f, s->xbuf[2], bit_left, g.lead + dst_from_right * stride, count, n_left, 0, st);
+    if (e == cudaSuccess) e = launch_planes(s, f, s->xbuf[3], bit_right, g.lead + dst_from_left * stride, count, n_right, 0, st);
     if (e != cudaSuccess) return set_error(-(int)e, "halo unpack", cudaGetErrorString(e));
     return 0;
 }
@@ -1322,6 +1331,12 @@ static int one_step(lbm_sim* s, void* f, void* fnew, double t, cudaStream_t st) 
         s->aa_even_walled = (!s->aa_swapped && s->aa_walls_fn) ? 1 : 0;
         if (ev1) cudaEventRecord(ev1, st);
         s->launches += 1;
+        if (!s->aa_swapped && s->nranks > 1) {
+            // x-slabs: what left through the slab faces sits in my ghost planes; the neighbours read it in
+            // their own swapped slots during the odd step
+            rc = exchange_slabs(s, f, st, true);
+            if (rc) return rc;
+        }
         s->aa_swapped ^= 1;
         s->ghost_fresh = s->aa_swapped ? 0 : 1;     // the odd kernel wrote the images of the next even step
         return 0;
@@ -1587,6 +1602,7 @@ extern "C" int lbm_sim_ipc_open(lbm_sim* s, const void* left_blob, const void* r
     if (!s || !left_blob || !right_blob) return ARG_ERROR("lbm_sim_ipc_open");
     if (!s->d.one_time_step_peers) return ARG_ERROR("the kernel library has no lbmk_one_time_step_peers");
     if (s->nranks < 2 || !s->flags) return ARG_ERROR("lbm_sim_ipc_open needs lbm_sim_comm_init and lbm_sim_ipc_export first");
+    if (s->aa_fn) return ARG_ERROR("lbm_sim_ipc_open: in-place streaming uses the NCCL halo");
     const void* blobs[2] = {left_blob, right_blob};
     const bool same = (s->nranks == 2);   // both neighbours are the same process: open its handles once
     for (int side = 0; side < 2; ++side) {
@@ -1611,7 +1627,7 @@ extern "C" int lbm_sim_ipc_open(lbm_sim* s, const void* left_blob, const void* r
 
 extern "C" int lbm_sim_comm_init(lbm_sim* s, int rank, int nranks, const void* id128) {
     if (!s || nranks < 1 || rank < 0 || rank >= nranks) return ARG_ERROR("lbm_sim_comm_init");
-    if (s->aa_fn && nranks > 1) return ARG_ERROR("lbm_sim_comm_init: in-place streaming is single GPU only");
+    if (s->aa_fn) return ARG_ERROR("lbm_sim_comm_init: call it before lbm_sim_set_aa");
     s->rank = rank;
     s->nranks = nranks;
     if (nranks == 1) return 0;

@@ -156,8 +156,9 @@ class CudaEngine:
     def _engine_defaults(self, storage, compute, slab=None, nccl_id=None, gather=None, in_place=False):
         self.storage, self.compute = storage, compute
         self.in_place = bool(in_place)
-        if self.in_place and slab is not None and slab[1] > 1:
-            raise ValueError("in-place streaming (in_place=True) runs on one GPU")
+        if self.in_place and slab is not None and slab[1] > 1 and gather is not None:
+            raise ValueError("in-place streaming on several GPUs uses the NCCL halo (no `gather` / halo='nccl'): "
+                             "the fused NVLink halo stores into the neighbours' second array")
         self.rank, self.nranks = slab if slab is not None else (0, 1)
         self._nccl_id, self._gather = nccl_id, gather
         self._mc_version = -1

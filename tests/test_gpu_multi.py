@@ -295,3 +295,60 @@ def test_pylbm_simulation_on_slabs(case, kw):
         whole = np.concatenate([results[r][str(key)] for r in range(world)], axis=0)
         full = ref.m[key]
         assert np.abs(whole[fluid] - full[fluid]).max() <= 1e-12 * np.abs(full[fluid]).max()
+
+
+def _aa_worker(rank, world, nccl_id, case, kw, nsteps, queue):
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
+    import pylbm_b200
+    from pylbm_b200 import cases, runtime as rt
+
+    rt.check(rt.lib().lbm_set_device(rank), "lbm_set_device")
+    sim = pylbm_b200.Simulation(cases.CASES[case](perturb=cases.WAVE, **kw), slab=(rank, world), nccl_id=nccl_id,
+                                in_place=True)
+    assert sim.container.Fnew is sim.container.F
+    for _ in range(3):
+        sim.one_time_step()
+    sim.boundary_condition()
+    sim.run(nsteps - 3)
+    out = {"F%d" % k: sim.F[k].copy() for k in range(sim.container.nv)}
+    out["swapped"] = sim._swapped
+    sim.synchronize()
+    queue.put((rank, out))
+
+
+@pytest.mark.parametrize("case,kw,nsteps", [("karman_d2q9", dict(nx=128, ny=32), 12), ("lid_cavity_d3q19", dict(n=16), 9),
+                                            ("shallow_water_d2q4", dict(n=32), 7)])
+def test_in_place_streaming_on_slabs(case, kw, nsteps, monkeypatch):
+    """in-place streaming (ONE array per GPU) on x-slabs with the NCCL halo: forward exchange before an even
+    step, reverse exchange (ghost planes -> the neighbours' interior planes) after it; the protocol is
+    proven in tests/test_aa_slabs_emulation.py.  Fluid populations IDENTICAL to the single-GPU two-array
+    run of the same kernel library, after even and odd step counts."""
+    import ctypes
+    import multiprocessing as mp
+
+    import pylbm_b200
+    from pylbm_b200 import cases, runtime as rt
+
+    ngpu = rt.lib().lbm_device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if ngpu < 4 else 4
+    raw = (ctypes.c_char * 128)()
+    rt.check(rt.lib().lbm_comm_unique_id(raw), "lbm_comm_unique_id")
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    procs = [ctx.Process(target=_aa_worker, args=(r, world, bytes(raw.raw), case, kw, nsteps, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(queue.get(timeout=600) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    monkeypatch.setenv("PYLBM_B200_AA_LIBRARY", "1")
+    ref = pylbm_b200.Simulation(cases.CASES[case](perturb=cases.WAVE, **kw))
+    ref.run(nsteps)
+    fluid = ref.domain.in_or_out[tuple(slice(v, -v) for v in ref.domain.stencil.vmax)] == ref.domain.valin
+    assert results[0]["swapped"] == bool(nsteps % 2)
+    for k in range(ref.container.nv):
+        whole = np.concatenate([results[r]["F%d" % k] for r in range(world)], axis=0)
+        assert np.array_equal(whole[fluid], ref.F[k][fluid]), "population %d" % k
