@@ -138,3 +138,101 @@ def test_directed_in_place_configurations(name):
     dico, _ = emu._directed_cases()[name]
     rng = np.random.default_rng(5)
     assert _check(dico, rng), "every directed configuration is expected to run in place"
+
+
+# ---------------------------------------------------------------------------
+# in place + the fused walls of the fastest axis (boundary.plan_walls)
+# ---------------------------------------------------------------------------
+def _run_aa_walls(lay, vel, sym, methods, odd_methods, walls, masks, nsteps, f0):
+    """the in-place scheme with the wall plan: the replaced entries run only on stale ghosts (first step);
+    the even kernel stores `+-f_k(c) + rhs[k]` into the cell's OWN slot (k, c), the odd kernel into the
+    wall's ghost cell (sym k, c + v_k), and neither keeps a periodic image along the fastest axis."""
+    q = len(vel)
+    n, w = lay.canonical_n, lay.canonical_vmax
+    vel3 = np.zeros((q, 3), dtype=int)
+    vel3[:, 3 - lay.dim:] = vel[:, : lay.dim]
+    inner = tuple(slice(w[a], n[a] - w[a]) for a in range(3))
+    idx = np.meshgrid(*[np.arange(w[a], n[a] - w[a]) for a in range(3)], indexing="ij")
+    i0, i1 = np.meshgrid(np.arange(w[0], n[0] - w[0]), np.arange(w[1], n[1] - w[1]), indexing="ij")
+    A = f0.copy()
+    natural, fresh = True, False
+    for _ in range(nsteps):
+        if natural:
+            if fresh:
+                emu._periodic(A, w, (0, 1), keep_fast_ghosts=True)
+            else:
+                emu._periodic(A, w, (0, 1, 2))
+            for im, m in enumerate(methods):
+                emu._apply(A, m, ~masks[im])
+                if not fresh:
+                    emu._apply(A, m, masks[im])
+            pulled = [A[(k,) + tuple(slice(w[a] - vel3[k][a], n[a] - w[a] - vel3[k][a]) for a in range(3))].copy()
+                      for k in range(q)]
+            new = _collide(pulled)
+            for k in range(q):
+                tgt = [idx[a] + vel3[k][a] for a in range(3)]
+                A[(sym[k],) + tuple(tgt)] = new[k]
+                out = np.zeros(tgt[0].shape, dtype=bool)
+                wrapped = []
+                for a in range(3):
+                    nin = n[a] - 2 * w[a]
+                    o = ((tgt[a] < w[a]) | (tgt[a] >= n[a] - w[a])) if (a != 2 and w[a] > 0) else np.zeros(tgt[a].shape, bool)
+                    out |= o
+                    wrapped.append(np.where(o, (tgt[a] - w[a]) % max(nin, 1) + w[a], tgt[a]))
+                if out.any():
+                    A[(sym[k],) + tuple(t[out] for t in wrapped)] = new[k][out]
+            # walls, even step: the bounced value into the cell's own slot of population k
+            for k in range(q):
+                if vel3[k][2] == 0:
+                    continue
+                plane = walls["lo_plane"] if vel3[k][2] < 0 else walls["hi_plane"]
+                neg = walls["neg_lo"] if vel3[k][2] < 0 else walls["neg_hi"]
+                val = new[k][:, :, plane - w[2]]
+                A[k, i0, i1, plane] = (-val if neg else val) + walls["rhs"][k]
+            natural = False
+        else:
+            for im, m in enumerate(odd_methods):
+                emu._apply(A, m, ~masks[im])
+            pulled = [A[(sym[k],) + inner].copy() for k in range(q)]
+            new = _collide(pulled)
+            for k in range(q):
+                A[(k,) + inner] = new[k]
+            # walls, odd step: like the two-array walls kernel
+            for k in range(q):
+                if vel3[k][2] == 0:
+                    continue
+                plane = walls["lo_plane"] if vel3[k][2] < 0 else walls["hi_plane"]
+                neg = walls["neg_lo"] if vel3[k][2] < 0 else walls["neg_hi"]
+                val = new[k][:, :, plane - w[2]]
+                A[sym[k], i0 + vel3[k][0], i1 + vel3[k][1], plane + vel3[k][2]] = (-val if neg else val) + walls["rhs"][k]
+            natural, fresh = True, True
+    if not natural:
+        S = np.zeros_like(A)
+        for k in range(q):
+            S[(k,) + inner] = A[(sym[k],) + tuple(idx[a] + vel3[k][a] for a in range(3))]
+        return S
+    return A
+
+
+@pytest.mark.parametrize("dim,seed", [(2, s) for s in range(60)] + [(3, s) for s in range(25)])
+def test_in_place_streaming_with_the_wall_plan(dim, seed):
+    from pylbm_b200.boundary import plan_aa
+
+    rng = np.random.default_rng(1000 * dim + seed)
+    dico = emu._random_case(rng, dim)
+    if not dico["boundary_conditions"]:
+        pytest.skip("fully periodic box")
+    dom, lay, vel, sym, methods, plan = emu._setup(dico)
+    if plan is None:
+        pytest.skip("wall plan refused")
+    walls, masks = plan
+    odd = plan_aa(methods, lay, vel, sym)
+    assert odd is not None
+    q = len(vel)
+    f0 = 1.0 / q + 0.05 * rng.uniform(-1, 1, size=(q,) + tuple(lay.canonical_n))
+    w, n = lay.canonical_vmax, lay.canonical_n
+    inner = (slice(None),) + tuple(slice(w[i], n[i] - w[i]) for i in range(3))
+    for nsteps in (4, 5):
+        a = emu._run(dom, lay, vel, sym, methods, None, nsteps, f0)
+        b = _run_aa_walls(lay, vel, sym, methods, odd, walls, masks, nsteps, f0)
+        assert np.array_equal(a[inner], b[inner]), nsteps
